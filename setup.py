@@ -1,0 +1,59 @@
+"""Build script of torch_cgx_b200 (sm_100a only).
+
+    python setup.py build_ext --inplace     # in-tree build: torch_cgx_b200/_C*.so
+    pip install --no-build-isolation .       # regular install
+
+Counterpart of the reference's setup.py (/root/reference/setup.py:1-93) minus
+MPI/ROCm: the only native dependencies are the CUDA runtime and libtorch.
+"""
+import os
+from pathlib import Path
+
+from setuptools import find_packages, setup
+from torch.utils.cpp_extension import BuildExtension, CUDAExtension
+
+ROOT = Path(__file__).parent.resolve()
+CSRC = Path("torch_cgx_b200") / "csrc"
+
+SOURCES = [
+    "common/plan.cc",
+    "common/config.cc",
+    "common/layers.cc",
+    "common/sra_sim.cc",
+    "comm/symmetric_heap.cc",
+    "reduce/fused_sra.cc",
+    "engine/engine.cc",
+    "kernels/sra_fused.cu",
+    "kernels/quantize.cu",
+    "pg/process_group_cgx.cc",
+    "bindings.cc",
+]
+
+# explicit -gencode: torch's own arch list is bypassed when one is present
+NVCC_FLAGS = [
+    "-O3",
+    "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "--fmad=false",  # the CPU oracle must be bit-exact: FMAs are written explicitly (quant_math.h)
+    "-Xptxas", "-v",
+]
+CXX_FLAGS = ["-O3", "-std=c++17", "-ffp-contract=off", "-Wno-unused-function"]
+
+os.environ.setdefault("MAX_JOBS", str(os.cpu_count() or 4))
+
+setup(
+    name="torch_cgx_b200",
+    version="0.1.0",
+    description="Blackwell-native compressed-gradient allreduce backend for torch.distributed",
+    packages=find_packages(include=["torch_cgx_b200*", "torch_cgx", "cgx_utils"]),
+    ext_modules=[
+        CUDAExtension(
+            name="torch_cgx_b200._C",
+            sources=[str(CSRC / s) for s in SOURCES],
+            extra_compile_args={"cxx": CXX_FLAGS, "nvcc": NVCC_FLAGS},
+        )
+    ],
+    cmdclass={"build_ext": BuildExtension.with_options(use_ninja=True, no_python_abi_suffix=False)},
+    python_requires=">=3.10",
+)

@@ -1,0 +1,82 @@
+// Symmetric peer-mapped device heap: the B200 replacement for the reference's
+// three point-to-point transports. Every rank owns ONE cudaMalloc'ed region
+//   [flags1][flags2][recv1: W slots][recv2: W slots]
+// and maps every peer's region into its own address space (CUDA IPC between
+// processes, plain pointers inside one process), so kernels move data with
+// ordinary ld/st over NVLink 5 / NVSwitch and signal with release/acquire
+// flags -- no host staging, no semaphores, no MPI.
+//
+// Replaces: SHMCommunicator + shm_utils (POSIX shm + named semaphores + IPC
+// events, GPU->pinned host->GPU over PCIe; /root/reference/src/common/
+// shm_communicator.cc:54-330, shm_utils.cc:51-136), MPICommunicator
+// (/root/reference/src/common/mpi_communicator.cc:24-84), PersistentBuffer
+// (/root/reference/src/common/buffer.cc:23-31) and the NCCL bootstrap
+// (/root/reference/src/common/nccl_reduce.cc:52-67). Handles travel through
+// the c10d Store (KVStore below) instead of MPI messages.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace cgx {
+
+struct HeapLayout {
+  int world = 1;
+  uint32_t flag_stride = 0;  // lanes capacity (multiple of 32)
+  uint32_t slot_bytes = 0;   // bytes per (source rank) slot, multiple of 256
+  size_t flags1_off = 0, flags2_off = 0, recv1_off = 0, recv2_off = 0, total = 0;
+  static HeapLayout make(int world, int max_lanes, size_t slot_bytes);
+};
+
+// Minimal key-value rendezvous (implemented over c10d::Store by the backend,
+// over a std::map by in-process tests).
+class KVStore {
+ public:
+  virtual ~KVStore() = default;
+  virtual void set(const std::string& key, const std::vector<uint8_t>& value) = 0;
+  virtual std::vector<uint8_t> get(const std::string& key) = 0;  // blocks until present
+};
+
+class SymmetricHeap {
+ public:
+  SymmetricHeap(int rank, int world, const HeapLayout& layout);
+  ~SymmetricHeap();
+  SymmetricHeap(const SymmetricHeap&) = delete;
+  SymmetricHeap& operator=(const SymmetricHeap&) = delete;
+
+  // peers live in this process (tests / single-process multi-stream simulation)
+  void connect_local(const std::vector<SymmetricHeap*>& all);
+  // one process per GPU: exchange cudaIpcMemHandles through the store
+  void connect_ipc(KVStore& store, const std::string& prefix);
+
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+  int device() const { return device_; }
+  const HeapLayout& layout() const { return layout_; }
+  bool connected() const { return connected_; }
+
+  uint8_t* base(int peer) const { return bases_[peer]; }
+  uint8_t* recv1(int peer) const { return bases_[peer] + layout_.recv1_off; }
+  uint8_t* recv2(int peer) const { return bases_[peer] + layout_.recv2_off; }
+  uint32_t* flags1(int peer) const { return reinterpret_cast<uint32_t*>(bases_[peer] + layout_.flags1_off); }
+  uint32_t* flags2(int peer) const { return reinterpret_cast<uint32_t*>(bases_[peer] + layout_.flags2_off); }
+
+  // host-visible error word written by kernels on timeout
+  uint32_t* status_device() const { return status_dev_; }
+  uint32_t status_host() const { return status_host_ ? *(volatile uint32_t*)status_host_ : 0; }
+  void clear_status() { if (status_host_) *(volatile uint32_t*)status_host_ = 0; }
+
+ private:
+  int rank_, world_, device_ = 0;
+  HeapLayout layout_;
+  std::vector<uint8_t*> bases_;   // [world]; bases_[rank_] is the local allocation
+  std::vector<bool> ipc_opened_;
+  uint32_t* status_host_ = nullptr;
+  uint32_t* status_dev_ = nullptr;
+  bool connected_ = false;
+};
+
+void cuda_check(cudaError_t e, const char* what);
+
+}  // namespace cgx

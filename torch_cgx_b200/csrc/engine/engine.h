@@ -1,0 +1,76 @@
+// Allreduce orchestration: layer extraction, compress / no-compress decision,
+// tensor-fusion chunking, dispatch to a reducer.
+//
+// Reference: MPIAllReduce_Operation (/root/reference/src/mpi_allreduce_operations
+// .h:34-85, .cc:117-287). Differences by design: compressed and uncompressed
+// layers of a bucket go through the SAME kernel launch (raw blocks) instead of
+// two reducer passes; the plan is cached per layout; nothing here touches MPI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+#include "../comm/symmetric_heap.h"
+#include "../common/config.h"
+#include "../common/layers.h"
+#include "../reduce/fused_sra.h"
+
+namespace cgx {
+
+struct EngineStats {
+  uint64_t calls = 0;            // allreduce calls
+  uint64_t kernel_launches = 0;  // fused kernel launches
+  uint64_t elements = 0;
+  uint64_t wire_bytes = 0;       // bytes this rank pushed over NVLink (both phases)
+  uint64_t raw_bytes = 0;        // bytes an uncompressed SRA would have pushed
+};
+
+// Split a layer list into groups whose raw size fits `fusion_bytes`
+// (Horovod-style tensor fusion threshold; a single layer larger than the
+// threshold is sliced at bucket boundaries). Unlike the reference
+// (mpi_allreduce_operations.cc:201-227) no trailing group is
+// ever dropped.
+std::vector<std::vector<LayerSpec>> split_for_fusion(const std::vector<LayerSpec>& layers, int elsize,
+                                                     int64_t fusion_bytes);
+
+class AllreduceEngine {
+ public:
+  AllreduceEngine(int rank, int world, const EngineConfig& cfg);
+  ~AllreduceEngine();
+
+  const EngineConfig& config() const { return cfg_; }
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+
+  // slot size the symmetric heap needs for this config
+  static size_t required_slot_bytes(const EngineConfig& cfg, int world);
+
+  // takes ownership of a connected heap and enables the fused P2P path
+  void attach_heap(std::unique_ptr<SymmetricHeap> heap, int lanes);
+  bool has_p2p() const { return fused_ != nullptr; }
+  SymmetricHeap* heap() { return heap_.get(); }
+  FusedSra* fused() { return fused_.get(); }
+
+  // In-place SUM (or AVG) allreduce of a CUDA buffer on `stream`.
+  //  explicit_bucket: DDP bucket index if the caller knows it, else -1.
+  void allreduce_cuda(void* data, int dtype, int64_t numel, bool average, int explicit_bucket,
+                      cudaStream_t stream);
+  // Same, with an explicit layer list (offsets relative to `data`).
+  void allreduce_cuda_layers(void* data, int dtype, const std::vector<LayerSpec>& layers, bool average,
+                             const CompressionEnv& env, cudaStream_t stream);
+
+  void check_health();
+  const EngineStats& stats() const { return stats_; }
+  void reset_stats() { stats_ = EngineStats(); }
+
+ private:
+  int rank_, world_;
+  EngineConfig cfg_;
+  std::unique_ptr<SymmetricHeap> heap_;
+  std::unique_ptr<FusedSra> fused_;
+  uint32_t call_seq_ = 0;
+  EngineStats stats_;
+};
+
+}  // namespace cgx

@@ -1,0 +1,349 @@
+#include "process_group_cgx.h"
+
+#include <c10/cuda/CUDACachingAllocator.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "../kernels/launch.h"
+
+namespace cgx {
+
+namespace {
+
+int to_cgx_dtype(at::ScalarType t) {
+  switch (t) {
+    case at::kFloat: return kF32;
+    case at::kHalf: return kF16;
+    case at::kBFloat16: return kBF16;
+    default: return -1;
+  }
+}
+
+// KVStore over the c10d Store handed to the backend
+class C10dKV : public KVStore {
+ public:
+  explicit C10dKV(c10::intrusive_ptr<c10d::Store> s) : s_(std::move(s)) {}
+  void set(const std::string& key, const std::vector<uint8_t>& value) override { s_->set(key, value); }
+  std::vector<uint8_t> get(const std::string& key) override { return s_->get(key); }
+
+ private:
+  c10::intrusive_ptr<c10d::Store> s_;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------- WorkCGX ---
+WorkCGX::WorkCGX(int rank, c10d::OpType op, const char* title, std::vector<at::Tensor> outputs,
+                 c10::Device device, c10::cuda::CUDAStream comm_stream)
+    : c10d::Work(rank, op, title, std::optional<std::vector<at::Tensor>>(outputs)),
+      outputs_(std::move(outputs)),
+      device_(device),
+      comm_stream_(comm_stream),
+      end_event_(cudaEventDisableTiming) {
+  future_ = c10::make_intrusive<c10::ivalue::Future>(c10::ListType::create(c10::TensorType::get()),
+                                                     std::vector<c10::Device>{device_});
+}
+
+void WorkCGX::finish_on_stream() {
+  end_event_.record(comm_stream_);
+  {
+    // the Future records its own events on the *current* stream of its devices:
+    // make that the comm stream so .then() callbacks / wait() order after the kernel
+    c10::cuda::CUDAStreamGuard g(comm_stream_);
+    future_->markCompleted(at::IValue(outputs_));
+  }
+  finish();  // completed_ = true (the GPU work itself is tracked by end_event_)
+}
+
+bool WorkCGX::isCompleted() { return end_event_.query(); }
+bool WorkCGX::isSuccess() const { return true; }
+void WorkCGX::synchronize() { end_event_.block(c10::cuda::getCurrentCUDAStream(device_.index())); }
+bool WorkCGX::wait(std::chrono::milliseconds /*timeout*/) {
+  // CUDA semantics of c10d: make the caller's current stream wait, never block the host
+  synchronize();
+  return true;
+}
+std::vector<at::Tensor> WorkCGX::result() { return outputs_; }
+c10::intrusive_ptr<c10::ivalue::Future> WorkCGX::getFuture() { return future_; }
+
+// -------------------------------------------------------- ProcessGroupCGX ---
+ProcessGroupCGX::ProcessGroupCGX(const c10::intrusive_ptr<c10d::Store>& store, int rank, int size,
+                                 std::chrono::milliseconds timeout,
+                                 c10::intrusive_ptr<c10d::Backend> cpu_delegate,
+                                 c10::intrusive_ptr<c10d::Backend> cuda_delegate)
+    : c10d::Backend(rank, size),
+      store_(store),
+      timeout_(timeout),
+      cpu_delegate_(std::move(cpu_delegate)),
+      cuda_delegate_(std::move(cuda_delegate)),
+      cfg_(EngineConfig::read()) {
+  TORCH_CHECK(size >= 1 && size <= kMaxPeers || cfg_.inner_comm != CommType::kP2P,
+              "cgx: the P2P path supports at most ", kMaxPeers, " ranks per node");
+  log_msg(1, "cgx[%d/%d]: backend created (inner=%s/%s fusion=%lld MB lanes=%d)", rank, size,
+          to_string(cfg_.inner_comm), to_string(cfg_.inner_reduction), (long long)(cfg_.fusion_bytes >> 20),
+          cfg_.lanes);
+}
+
+ProcessGroupCGX::~ProcessGroupCGX() {
+  if (engine_ && device_ >= 0) {
+    c10::cuda::CUDAGuard g(device_);
+    cudaDeviceSynchronize();
+    engine_.reset();
+  }
+}
+
+c10::intrusive_ptr<c10d::Backend> ProcessGroupCGX::delegate_for(const at::Tensor& t, const char* op) {
+  if (t.is_cuda()) {
+    TORCH_CHECK(cuda_delegate_, "cgx: no CUDA delegate backend available for ", op);
+    return cuda_delegate_;
+  }
+  TORCH_CHECK(cpu_delegate_, "cgx: no CPU delegate backend available for ", op);
+  return cpu_delegate_;
+}
+
+bool ProcessGroupCGX::eligible_for_engine(const at::Tensor& t, const c10d::ReduceOp& op) const {
+  // reference: do_compress = (fp16|fp32) && SUM && CUDA  (ProcessGroupCGX.cc:374-377); bf16 and AVG added
+  if (!t.is_cuda() || cfg_.inner_comm != CommType::kP2P) return false;
+  if (to_cgx_dtype(t.scalar_type()) < 0) return false;
+  if (!(op == c10d::ReduceOp::SUM || op == c10d::ReduceOp::AVG)) return false;
+  if (!t.is_non_overlapping_and_dense()) return false;
+  if (getSize() > kMaxPeers) return false;
+  return true;
+}
+
+void ProcessGroupCGX::init_cuda(int64_t device_index) { ensure_cuda((c10::DeviceIndex)device_index); }
+
+void ProcessGroupCGX::ensure_cuda(c10::DeviceIndex dev) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (engine_) {
+    TORCH_CHECK(dev == device_, "cgx: this process group is bound to cuda:", (int)device_,
+                " but got a tensor on cuda:", (int)dev);
+    return;
+  }
+  c10::cuda::CUDAGuard g(dev);
+  device_ = dev;
+  comm_stream_ = c10::cuda::getStreamFromPool(/*isHighPriority=*/true, dev);
+  start_event_.emplace(cudaEventDisableTiming);
+  auto engine = std::make_unique<AllreduceEngine>(getRank(), getSize(), cfg_);
+
+  // agree on the number of lanes (CTAs): min over ranks of what can be co-resident
+  int resident = sra_max_resident_ctas(kF32);
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int want = cfg_.lanes > 0 ? cfg_.lanes : sms;
+  int mine = std::max(1, std::min(want, resident));
+  C10dKV kv(store_);
+  const std::string prefix = "cgx/p2p";
+  {
+    std::vector<uint8_t> v(sizeof(int));
+    std::memcpy(v.data(), &mine, sizeof(int));
+    kv.set(prefix + "/lanes/" + std::to_string(getRank()), v);
+  }
+  int lanes = mine;
+  for (int p = 0; p < getSize(); ++p) {
+    if (p == getRank()) continue;
+    auto v = kv.get(prefix + "/lanes/" + std::to_string(p));
+    int other = 0;
+    std::memcpy(&other, v.data(), sizeof(int));
+    lanes = std::min(lanes, other);
+  }
+  HeapLayout layout =
+      HeapLayout::make(getSize(), lanes, AllreduceEngine::required_slot_bytes(cfg_, getSize()));
+  auto heap = std::make_unique<SymmetricHeap>(getRank(), getSize(), layout);
+  if (getSize() > 1) heap->connect_ipc(kv, prefix);
+  engine->attach_heap(std::move(heap), lanes);
+  engine_ = std::move(engine);
+  log_msg(1, "cgx[%d]: P2P engine ready on cuda:%d (lanes=%d, heap=%.1f MB, slot=%u B)", getRank(), (int)dev,
+          lanes, (double)layout.total / (1 << 20), layout.slot_bytes);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::engine_allreduce(at::Tensor& t, bool average, int bucket_idx) {
+  const c10::DeviceIndex dev = t.device().index();
+  ensure_cuda(dev);
+  c10::cuda::CUDAGuard g(dev);
+  auto cur = c10::cuda::getCurrentCUDAStream(dev);
+  auto work = c10::make_intrusive<WorkCGX>(getRank(), c10d::OpType::ALLREDUCE, "cgx:all_reduce",
+                                           std::vector<at::Tensor>{t}, t.device(), *comm_stream_);
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    ++seq_;
+    // order after the producer of `t` on the caller's stream
+    start_event_->record(cur);
+    start_event_->block(*comm_stream_);
+    // the caching allocator must not hand this memory out while the comm stream uses it
+    c10::cuda::CUDACachingAllocator::recordStream(t.storage().data_ptr(), *comm_stream_);
+    engine_->allreduce_cuda(t.data_ptr(), to_cgx_dtype(t.scalar_type()), t.numel(), average, bucket_idx,
+                            comm_stream_->stream());
+    work->finish_on_stream();
+  }
+  return work;
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::allreduce(std::vector<at::Tensor>& tensors,
+                                                          const c10d::AllreduceOptions& opts) {
+  TORCH_CHECK(tensors.size() == 1, "cgx: allreduce expects exactly one tensor");
+  at::Tensor& t = tensors[0];
+  if (eligible_for_engine(t, opts.reduceOp)) {
+    return engine_allreduce(t, opts.reduceOp == c10d::ReduceOp::AVG, -1);
+  }
+  return delegate_for(t, "allreduce")->allreduce(tensors, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::allreduce_bucket(at::Tensor& tensor, int64_t bucket_idx,
+                                                                 bool average) {
+  c10d::ReduceOp op = average ? c10d::ReduceOp::AVG : c10d::ReduceOp::SUM;
+  if (eligible_for_engine(tensor, op)) return engine_allreduce(tensor, average, (int)bucket_idx);
+  std::vector<at::Tensor> ts{tensor};
+  c10d::AllreduceOptions o;
+  if (average && !tensor.is_cuda()) {
+    // Gloo has no AVG: pre-divide like the reference hook does
+    tensor.div_(getSize());
+    o.reduceOp = c10d::ReduceOp::SUM;
+  } else {
+    o.reduceOp = op;
+  }
+  return delegate_for(tensor, "allreduce")->allreduce(ts, o);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::allreduce_coalesced(std::vector<at::Tensor>& tensors,
+                                                                    const c10d::AllreduceCoalescedOptions& opts) {
+  TORCH_CHECK(!tensors.empty(), "cgx: allreduce_coalesced needs tensors");
+  return delegate_for(tensors[0], "allreduce_coalesced")->allreduce_coalesced(tensors, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::broadcast(std::vector<at::Tensor>& tensors,
+                                                          const c10d::BroadcastOptions& opts) {
+  TORCH_CHECK(!tensors.empty(), "cgx: broadcast needs tensors");
+  return delegate_for(tensors[0], "broadcast")->broadcast(tensors, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::reduce(std::vector<at::Tensor>& tensors,
+                                                       const c10d::ReduceOptions& opts) {
+  TORCH_CHECK(!tensors.empty(), "cgx: reduce needs tensors");
+  return delegate_for(tensors[0], "reduce")->reduce(tensors, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::allgather(std::vector<std::vector<at::Tensor>>& outputTensors,
+                                                          std::vector<at::Tensor>& inputTensors,
+                                                          const c10d::AllgatherOptions& opts) {
+  TORCH_CHECK(!inputTensors.empty(), "cgx: allgather needs tensors");
+  return delegate_for(inputTensors[0], "allgather")->allgather(outputTensors, inputTensors, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::_allgather_base(at::Tensor& outputBuffer, at::Tensor& inputBuffer,
+                                                                const c10d::AllgatherOptions& opts) {
+  return delegate_for(inputBuffer, "_allgather_base")->_allgather_base(outputBuffer, inputBuffer, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::allgather_coalesced(
+    std::vector<std::vector<at::Tensor>>& outputTensorLists, std::vector<at::Tensor>& inputTensors,
+    const c10d::AllgatherOptions& opts) {
+  TORCH_CHECK(!inputTensors.empty(), "cgx: allgather_coalesced needs tensors");
+  return delegate_for(inputTensors[0], "allgather_coalesced")
+      ->allgather_coalesced(outputTensorLists, inputTensors, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::allgather_into_tensor_coalesced(
+    std::vector<at::Tensor>& outputs, std::vector<at::Tensor>& inputs, const c10d::AllgatherOptions& opts) {
+  TORCH_CHECK(!inputs.empty(), "cgx: allgather_into_tensor_coalesced needs tensors");
+  return delegate_for(inputs[0], "allgather_into_tensor_coalesced")
+      ->allgather_into_tensor_coalesced(outputs, inputs, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::gather(std::vector<std::vector<at::Tensor>>& outputTensors,
+                                                       std::vector<at::Tensor>& inputTensors,
+                                                       const c10d::GatherOptions& opts) {
+  TORCH_CHECK(!inputTensors.empty(), "cgx: gather needs tensors");
+  return delegate_for(inputTensors[0], "gather")->gather(outputTensors, inputTensors, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::scatter(std::vector<at::Tensor>& outputTensors,
+                                                        std::vector<std::vector<at::Tensor>>& inputTensors,
+                                                        const c10d::ScatterOptions& opts) {
+  TORCH_CHECK(!outputTensors.empty(), "cgx: scatter needs tensors");
+  return delegate_for(outputTensors[0], "scatter")->scatter(outputTensors, inputTensors, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::reduce_scatter(std::vector<at::Tensor>& outputTensors,
+                                                               std::vector<std::vector<at::Tensor>>& inputTensors,
+                                                               const c10d::ReduceScatterOptions& opts) {
+  TORCH_CHECK(!outputTensors.empty(), "cgx: reduce_scatter needs tensors");
+  return delegate_for(outputTensors[0], "reduce_scatter")->reduce_scatter(outputTensors, inputTensors, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::_reduce_scatter_base(at::Tensor& outputBuffer,
+                                                                     at::Tensor& inputBuffer,
+                                                                     const c10d::ReduceScatterOptions& opts) {
+  return delegate_for(inputBuffer, "_reduce_scatter_base")->_reduce_scatter_base(outputBuffer, inputBuffer, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::reduce_scatter_tensor_coalesced(
+    std::vector<at::Tensor>& outputs, std::vector<at::Tensor>& inputs, const c10d::ReduceScatterOptions& opts) {
+  TORCH_CHECK(!inputs.empty(), "cgx: reduce_scatter_tensor_coalesced needs tensors");
+  return delegate_for(inputs[0], "reduce_scatter_tensor_coalesced")
+      ->reduce_scatter_tensor_coalesced(outputs, inputs, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::alltoall_base(at::Tensor& outputBuffer, at::Tensor& inputBuffer,
+                                                              std::vector<int64_t>& outputSplitSizes,
+                                                              std::vector<int64_t>& inputSplitSizes,
+                                                              const c10d::AllToAllOptions& opts) {
+  return delegate_for(inputBuffer, "alltoall_base")
+      ->alltoall_base(outputBuffer, inputBuffer, outputSplitSizes, inputSplitSizes, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::alltoall(std::vector<at::Tensor>& outputTensors,
+                                                         std::vector<at::Tensor>& inputTensors,
+                                                         const c10d::AllToAllOptions& opts) {
+  TORCH_CHECK(!inputTensors.empty(), "cgx: alltoall needs tensors");
+  return delegate_for(inputTensors[0], "alltoall")->alltoall(outputTensors, inputTensors, opts);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::send(std::vector<at::Tensor>& tensors, int dstRank, int tag) {
+  TORCH_CHECK(!tensors.empty(), "cgx: send needs tensors");
+  return delegate_for(tensors[0], "send")->send(tensors, dstRank, tag);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::recv(std::vector<at::Tensor>& tensors, int srcRank, int tag) {
+  TORCH_CHECK(!tensors.empty(), "cgx: recv needs tensors");
+  return delegate_for(tensors[0], "recv")->recv(tensors, srcRank, tag);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::recvAnysource(std::vector<at::Tensor>& tensors, int tag) {
+  TORCH_CHECK(!tensors.empty(), "cgx: recvAnysource needs tensors");
+  return delegate_for(tensors[0], "recvAnysource")->recvAnysource(tensors, tag);
+}
+
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::barrier(const c10d::BarrierOptions& opts) {
+  // A barrier must also drain this backend's own side stream.
+  if (engine_ && device_ >= 0) {
+    c10::cuda::CUDAGuard g(device_);
+    comm_stream_->synchronize();
+    engine_->check_health();
+  }
+  const bool use_cuda = cuda_delegate_ && (opts.device.has_value() ? opts.device->is_cuda() : device_ >= 0);
+  if (use_cuda) return cuda_delegate_->barrier(opts);
+  TORCH_CHECK(cpu_delegate_, "cgx: no delegate backend available for barrier");
+  return cpu_delegate_->barrier(opts);
+}
+
+int64_t ProcessGroupCGX::lanes() const { return engine_ && engine_->has_p2p() ? engine_->fused()->max_lanes() : 0; }
+
+std::vector<int64_t> ProcessGroupCGX::stats() const {
+  if (!engine_) return {0, 0, 0, 0, 0};
+  const EngineStats& s = engine_->stats();
+  return {(int64_t)s.calls, (int64_t)s.kernel_launches, (int64_t)s.elements, (int64_t)s.wire_bytes,
+          (int64_t)s.raw_bytes};
+}
+
+void ProcessGroupCGX::reset_stats() {
+  if (engine_) engine_->reset_stats();
+}
+
+void ProcessGroupCGX::check_health() {
+  if (engine_) engine_->check_health();
+}
+
+}  // namespace cgx

@@ -1,0 +1,148 @@
+// torch.distributed backend "cgx".
+//
+// Capabilities mirror ProcessGroupCGX of the reference
+// (/root/reference/src/ProcessGroupCGX.h:105-317, .cc:269-833): allreduce of
+// CUDA fp16/fp32 (+bf16 here) SUM tensors goes through the compressed
+// allreduce engine on a dedicated side stream; everything else is forwarded
+// verbatim -- there to MPI, here to an internal Gloo (CPU tensors) or NCCL
+// (CUDA tensors) delegate, which also supplies the collectives the reference
+// throws on (reduce_scatter, _allgather_base, allreduce_coalesced).
+//
+// Architecture differences (B200-first):
+//  * no worker thread / FIFO queue on the CUDA path (reference .cc:300-339): the
+//    whole allreduce is ONE stream-ordered kernel launch, so the Work/Future is
+//    completed at enqueue time with CUDA events, like ProcessGroupNCCL;
+//  * the start event is recorded on the CALLER's current stream (the reference
+//    records on the worker thread's default stream -- SURVEY.md §2.8 #8) and
+//    every Work owns its end event;
+//  * rendezvous uses the c10d Store handed to the constructor (the reference
+//    ignores store/timeout and requires mpirun -- .cc:259-267).
+#pragma once
+#include <ATen/cuda/CUDAEvent.h>
+#include <c10/cuda/CUDAStream.h>
+#include <torch/csrc/distributed/c10d/Backend.hpp>
+#include <torch/csrc/distributed/c10d/Store.hpp>
+#include <torch/csrc/distributed/c10d/Work.hpp>
+
+#include <chrono>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "../engine/engine.h"
+
+namespace cgx {
+
+class WorkCGX : public c10d::Work {
+ public:
+  WorkCGX(int rank, c10d::OpType op, const char* title, std::vector<at::Tensor> outputs, c10::Device device,
+          c10::cuda::CUDAStream comm_stream);
+  bool isCompleted() override;
+  bool isSuccess() const override;
+  bool wait(std::chrono::milliseconds timeout = kNoTimeout) override;
+  void synchronize() override;
+  std::vector<at::Tensor> result() override;
+  c10::intrusive_ptr<c10::ivalue::Future> getFuture() override;
+  // record the end of the work on the comm stream and complete the future
+  void finish_on_stream();
+
+ private:
+  std::vector<at::Tensor> outputs_;
+  c10::Device device_;
+  c10::cuda::CUDAStream comm_stream_;
+  at::cuda::CUDAEvent end_event_;
+  c10::intrusive_ptr<c10::ivalue::Future> future_;
+};
+
+class ProcessGroupCGX : public c10d::Backend {
+ public:
+  ProcessGroupCGX(const c10::intrusive_ptr<c10d::Store>& store, int rank, int size,
+                  std::chrono::milliseconds timeout, c10::intrusive_ptr<c10d::Backend> cpu_delegate,
+                  c10::intrusive_ptr<c10d::Backend> cuda_delegate);
+  ~ProcessGroupCGX() override;
+
+  const std::string getBackendName() const override { return "cgx"; }
+
+  c10::intrusive_ptr<c10d::Work> allreduce(std::vector<at::Tensor>& tensors,
+                                           const c10d::AllreduceOptions& opts = c10d::AllreduceOptions()) override;
+  c10::intrusive_ptr<c10d::Work> allreduce_coalesced(
+      std::vector<at::Tensor>& tensors,
+      const c10d::AllreduceCoalescedOptions& opts = c10d::AllreduceCoalescedOptions()) override;
+  c10::intrusive_ptr<c10d::Work> broadcast(std::vector<at::Tensor>& tensors,
+                                           const c10d::BroadcastOptions& opts = c10d::BroadcastOptions()) override;
+  c10::intrusive_ptr<c10d::Work> reduce(std::vector<at::Tensor>& tensors,
+                                        const c10d::ReduceOptions& opts = c10d::ReduceOptions()) override;
+  c10::intrusive_ptr<c10d::Work> allgather(std::vector<std::vector<at::Tensor>>& outputTensors,
+                                           std::vector<at::Tensor>& inputTensors,
+                                           const c10d::AllgatherOptions& opts = c10d::AllgatherOptions()) override;
+  c10::intrusive_ptr<c10d::Work> _allgather_base(at::Tensor& outputBuffer, at::Tensor& inputBuffer,
+                                                 const c10d::AllgatherOptions& opts = c10d::AllgatherOptions()) override;
+  c10::intrusive_ptr<c10d::Work> allgather_coalesced(std::vector<std::vector<at::Tensor>>& outputTensorLists,
+                                                     std::vector<at::Tensor>& inputTensors,
+                                                     const c10d::AllgatherOptions& opts = c10d::AllgatherOptions()) override;
+  c10::intrusive_ptr<c10d::Work> allgather_into_tensor_coalesced(
+      std::vector<at::Tensor>& outputs, std::vector<at::Tensor>& inputs,
+      const c10d::AllgatherOptions& opts = c10d::AllgatherOptions()) override;
+  c10::intrusive_ptr<c10d::Work> gather(std::vector<std::vector<at::Tensor>>& outputTensors,
+                                        std::vector<at::Tensor>& inputTensors,
+                                        const c10d::GatherOptions& opts = c10d::GatherOptions()) override;
+  c10::intrusive_ptr<c10d::Work> scatter(std::vector<at::Tensor>& outputTensors,
+                                         std::vector<std::vector<at::Tensor>>& inputTensors,
+                                         const c10d::ScatterOptions& opts = c10d::ScatterOptions()) override;
+  c10::intrusive_ptr<c10d::Work> reduce_scatter(std::vector<at::Tensor>& outputTensors,
+                                                std::vector<std::vector<at::Tensor>>& inputTensors,
+                                                const c10d::ReduceScatterOptions& opts = c10d::ReduceScatterOptions()) override;
+  c10::intrusive_ptr<c10d::Work> _reduce_scatter_base(at::Tensor& outputBuffer, at::Tensor& inputBuffer,
+                                                      const c10d::ReduceScatterOptions& opts = c10d::ReduceScatterOptions()) override;
+  c10::intrusive_ptr<c10d::Work> reduce_scatter_tensor_coalesced(
+      std::vector<at::Tensor>& outputs, std::vector<at::Tensor>& inputs,
+      const c10d::ReduceScatterOptions& opts = c10d::ReduceScatterOptions()) override;
+  c10::intrusive_ptr<c10d::Work> alltoall_base(at::Tensor& outputBuffer, at::Tensor& inputBuffer,
+                                               std::vector<int64_t>& outputSplitSizes,
+                                               std::vector<int64_t>& inputSplitSizes,
+                                               const c10d::AllToAllOptions& opts = c10d::AllToAllOptions()) override;
+  c10::intrusive_ptr<c10d::Work> alltoall(std::vector<at::Tensor>& outputTensors,
+                                          std::vector<at::Tensor>& inputTensors,
+                                          const c10d::AllToAllOptions& opts = c10d::AllToAllOptions()) override;
+  c10::intrusive_ptr<c10d::Work> send(std::vector<at::Tensor>& tensors, int dstRank, int tag) override;
+  c10::intrusive_ptr<c10d::Work> recv(std::vector<at::Tensor>& tensors, int srcRank, int tag) override;
+  c10::intrusive_ptr<c10d::Work> recvAnysource(std::vector<at::Tensor>& tensors, int tag) override;
+  c10::intrusive_ptr<c10d::Work> barrier(const c10d::BarrierOptions& opts = c10d::BarrierOptions()) override;
+
+  void setSequenceNumberForGroup() override {}
+  uint64_t getSequenceNumberForGroup() override { return seq_; }
+
+  // ---- cgx-specific API (bound to Python) ----------------------------------
+  // allreduce of one DDP bucket whose index is known (no cursor guessing);
+  // average == true fuses the 1/world scale into the kernel.
+  c10::intrusive_ptr<c10d::Work> allreduce_bucket(at::Tensor& tensor, int64_t bucket_idx, bool average);
+  // force the lazy CUDA-side initialisation (heap allocation + IPC exchange)
+  void init_cuda(int64_t device_index);
+  bool p2p_ready() const { return engine_ && engine_->has_p2p(); }
+  int64_t lanes() const;
+  std::vector<int64_t> stats() const;  // calls, kernel launches, elements, wire bytes, raw bytes
+  void reset_stats();
+  void check_health();
+
+ private:
+  c10::intrusive_ptr<c10d::Backend> delegate_for(const at::Tensor& t, const char* op);
+  bool eligible_for_engine(const at::Tensor& t, const c10d::ReduceOp& op) const;
+  c10::intrusive_ptr<c10d::Work> engine_allreduce(at::Tensor& t, bool average, int bucket_idx);
+  void ensure_cuda(c10::DeviceIndex dev);
+
+  c10::intrusive_ptr<c10d::Store> store_;
+  std::chrono::milliseconds timeout_;
+  c10::intrusive_ptr<c10d::Backend> cpu_delegate_;
+  c10::intrusive_ptr<c10d::Backend> cuda_delegate_;
+  EngineConfig cfg_;
+  std::unique_ptr<AllreduceEngine> engine_;
+  std::optional<c10::cuda::CUDAStream> comm_stream_;
+  std::optional<at::cuda::CUDAEvent> start_event_;
+  c10::DeviceIndex device_ = -1;
+  std::mutex mu_;
+  uint64_t seq_ = 0;
+};
+
+}  // namespace cgx

@@ -1,0 +1,99 @@
+#include "fused_sra.h"
+
+#include <stdexcept>
+#include <string>
+
+#include "../common/config.h"
+#include "../kernels/launch.h"
+
+namespace cgx {
+
+FusedSra::FusedSra(SymmetricHeap* heap, int max_lanes, int64_t timeout_ms, uint32_t min_lane_elems)
+    : heap_(heap), max_lanes_(max_lanes), timeout_ns_((uint64_t)timeout_ms * 1000000ull),
+      min_lane_elems_(min_lane_elems) {
+  if (max_lanes_ < 1) max_lanes_ = 1;
+  if ((uint32_t)max_lanes_ > heap_->layout().flag_stride) max_lanes_ = (int)heap_->layout().flag_stride;
+}
+
+FusedSra::~FusedSra() {
+  for (auto& kv : cache_) {
+    if (kv.second->d_blocks) cudaFree(kv.second->d_blocks);
+    if (kv.second->d_lane_first) cudaFree(kv.second->d_lane_first);
+  }
+}
+
+const DevicePlan* FusedSra::prepare(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
+                                    cudaStream_t stream) {
+  PlanOptions opt;
+  opt.world = world();
+  opt.lanes = max_lanes_;
+  opt.dtype = dtype;
+  opt.skip_incomplete = skip_incomplete;
+  opt.min_lane_elems = min_lane_elems_;
+  const uint64_t key = plan_key(layers, opt);
+  auto it = cache_.find(key);
+  if (it == cache_.end()) {
+    auto dp = std::make_unique<DevicePlan>();
+    dp->plan = build_plan(layers, opt);
+    if (dp->plan.max_chunk_wire <= heap_->layout().slot_bytes && !dp->plan.blocks.empty()) {
+      const size_t bb = dp->plan.blocks.size() * sizeof(BlockDesc);
+      const size_t lb = dp->plan.lane_first.size() * sizeof(uint32_t);
+      cuda_check(cudaMalloc((void**)&dp->d_blocks, bb), "cudaMalloc(plan blocks)");
+      cuda_check(cudaMalloc((void**)&dp->d_lane_first, lb), "cudaMalloc(plan lanes)");
+      // pageable source: the runtime stages it before returning, so the vectors may be reused
+      cuda_check(cudaMemcpyAsync(dp->d_blocks, dp->plan.blocks.data(), bb, cudaMemcpyHostToDevice, stream),
+                 "upload plan blocks");
+      cuda_check(cudaMemcpyAsync(dp->d_lane_first, dp->plan.lane_first.data(), lb, cudaMemcpyHostToDevice, stream),
+                 "upload plan lanes");
+    }
+    log_msg(2, "cgx[%d]: new plan %s", rank(), describe_plan(dp->plan).c_str());
+    it = cache_.emplace(key, std::move(dp)).first;
+  }
+  const DevicePlan* dp = it->second.get();
+  if (dp->plan.max_chunk_wire > heap_->layout().slot_bytes) return nullptr;
+  return dp;
+}
+
+void FusedSra::run(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream) {
+  if (!heap_->connected()) throw std::runtime_error("cgx: symmetric heap is not connected");
+  if (dp.plan.blocks.empty()) return;
+  ++epoch_;
+  SraParams p;
+  p.data = data;
+  p.blocks = dp.d_blocks;
+  p.lane_first = dp.d_lane_first;
+  p.rank = rank();
+  p.world = world();
+  p.lanes = dp.plan.lanes;
+  p.dtype = dp.plan.dtype;
+  p.epoch = epoch_;
+  p.prescale = prescale;
+  p.rng = make_rng_key(rng, rank(), 0);
+  p.slot_bytes = heap_->layout().slot_bytes;
+  p.flag_stride = heap_->layout().flag_stride;
+  for (int q = 0; q < kMaxPeers; ++q) {
+    const bool valid = q < world();
+    p.recv1[q] = valid ? heap_->recv1(q) : nullptr;
+    p.recv2[q] = valid ? heap_->recv2(q) : nullptr;
+    p.flags1[q] = valid ? heap_->flags1(q) : nullptr;
+    p.flags2[q] = valid ? heap_->flags2(q) : nullptr;
+  }
+  p.status = heap_->status_device();
+  p.timeout_ns = timeout_ns_;
+  cuda_check(launch_sra_fused(p, stream), "launch_sra_fused");
+  ++launches_;
+}
+
+void FusedSra::check_status() {
+  uint32_t s = heap_->status_host();
+  if (s == 0) return;
+  heap_->clear_status();
+  const uint32_t code = s & 0xFF, peer = (s >> 8) & 0xFF, lane = s >> 16;
+  throw std::runtime_error("cgx: fused allreduce kernel timed out on rank " + std::to_string(rank()) +
+                           " waiting for rank " + std::to_string(peer) + " (phase " + std::to_string(code) +
+                           ", lane " + std::to_string(lane) +
+                           "); a peer died, is stuck, or issued collectives in a different order "
+                           "(raise CGX_TIMEOUT_MS if the job is just slow)");
+}
+
+}  // namespace cgx

@@ -1,0 +1,60 @@
+// Host driver of the fused P2P Scatter-Reduce-AllGather kernel: plan cache,
+// epoch counter, launch. One instance per (process group, device).
+// Reference role: MPI_Allreduce_ScatterReduceAllgather::AllreduceCompressed /
+// AllreduceUncompressed (/root/reference/src/common/scatter_reduce_allgather.cc
+// :94-202, :308-413) and NCCL_Reduce (/root/reference/src/common/nccl_reduce.cc
+// :103-198) -- collapsed into a single kernel launch per call.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <memory>
+#include <unordered_map>
+#include <vector>
+
+#include "../comm/symmetric_heap.h"
+#include "../common/plan.h"
+#include "../common/sra_sim.h"
+
+namespace cgx {
+
+struct DevicePlan {
+  Plan plan;
+  BlockDesc* d_blocks = nullptr;
+  uint32_t* d_lane_first = nullptr;
+};
+
+class FusedSra {
+ public:
+  FusedSra(SymmetricHeap* heap, int max_lanes, int64_t timeout_ms, uint32_t min_lane_elems);
+  ~FusedSra();
+
+  int rank() const { return heap_->rank(); }
+  int world() const { return heap_->world(); }
+  int max_lanes() const { return max_lanes_; }
+
+  // Build (or fetch) the plan for `layers`; returns nullptr if its largest
+  // chunk does not fit the heap's slots (caller must split the call).
+  const DevicePlan* prepare(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
+                            cudaStream_t stream);
+
+  // In-place allreduce of `data` over the layers of `dp`. Stream-ordered, no
+  // host synchronisation. Every rank must call this the same number of times
+  // in the same order (epoch counter).
+  void run(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream);
+
+  // throws std::runtime_error if a kernel reported a timeout
+  void check_status();
+  uint64_t launches() const { return launches_; }
+  uint32_t epoch() const { return epoch_; }
+
+ private:
+  SymmetricHeap* heap_;
+  int max_lanes_;
+  uint64_t timeout_ns_;
+  uint32_t min_lane_elems_;
+  uint32_t epoch_ = 0;
+  uint64_t launches_ = 0;
+  std::unordered_map<uint64_t, std::unique_ptr<DevicePlan>> cache_;
+};
+
+}  // namespace cgx
