@@ -9,6 +9,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
+#include <pybind11/chrono.h>
 #include <torch/extension.h>
 
 #include <memory>

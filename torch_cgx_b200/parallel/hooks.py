@@ -15,7 +15,6 @@ B200-first differences:
    (``allreduce_bucket(tensor, bucket.index())``) instead of relying on a
    cyclic cursor over call order (/root/reference/src/mpi_allreduce_operations.cc:263-266).
 """
-from __future__ import annotations
 
 import os
 from typing import Dict, Optional
