@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Flagship benchmark: ResNet-50 DDP training step with the cgx comm hook
+(bits=4, bucket_size=512) -- BASELINE.json configs[1] -- on N B200s of one node.
+
+    python bench.py                                   # N=1, short
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29500 bench.py --gpus 8 --steps 20 --warmup 5
+
+One JSON line on rank 0 (contract in the task description):
+  value          whole-job images/s, device-timed (CUDA events, max over ranks), inputs resident
+  e2e.value      same step through the public API *including* the per-step H2D copy of the
+                 batch from pinned host memory and the D2H read of the loss
+  gpu_launches   launches of this repo's own fused allreduce kernel inside the timed region
+Other models of BASELINE.json: --model gpt2-medium | vit-l16 (tokens/s or images/s).
+--backend nccl runs the same script on stock NCCL DDP (same-box yardstick).
+--impl reference would run the unmodified reference from baseline/_ref; it cannot be
+installed on this image (needs OpenMPI: see DESIGN.md), so it reports `unavailable`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="cgx", choices=["cgx", "reference"])
+    p.add_argument("--backend", default="cgx", choices=["cgx", "nccl"])
+    p.add_argument("--model", default="resnet50", choices=["resnet50", "resnet18", "gpt2-medium", "gpt2-small", "vit-l16", "vit-b16"])
+    p.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = model default)")
+    p.add_argument("--seq-len", type=int, default=1024)
+    p.add_argument("--bits", type=int, default=-1, help="quantization bits (-1 = BASELINE config of the model)")
+    p.add_argument("--bucket-size", type=int, default=512)
+    p.add_argument("--layer-min-size", type=int, default=1024)
+    p.add_argument("--stochastic", type=int, default=-1)
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+MODEL_DEFAULTS = {
+    # model: (per-GPU batch, bits, stochastic, metric unit)
+    "resnet50": (128, 4, 0, "images/s"),
+    "resnet18": (256, 4, 0, "images/s"),
+    "gpt2-medium": (8, 8, 0, "tokens/s"),
+    "gpt2-small": (16, 8, 0, "tokens/s"),
+    "vit-l16": (32, 2, 1, "images/s"),
+    "vit-b16": (64, 2, 1, "images/s"),
+}
+
+
+def reference_unavailable():
+    why = "reference setup.py needs OpenMPI (ompi_info, -lmpi, mpi-ext.h); none in this image and no network -- see baseline/reference_install.log"
+    ref = ROOT / "baseline" / "_ref"
+    if ref.exists() and any(ref.glob("torch_cgx*.so")):
+        why = "baseline/_ref has a build but it needs mpirun + CUDA-aware MPI at run time, not present on this image"
+    print(json.dumps({"impl": "reference", "unavailable": why}))
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_unavailable()
+        return 0
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: relaunch under torchrun (the driver already does this itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
+        return subprocess.call(cmd)
+
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    import torch_cgx_b200 as cgx
+    from torch_cgx_b200 import models
+    from torch_cgx_b200.utils.data import CudaPrefetcher, SyntheticHostDataset
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if "MASTER_ADDR" not in os.environ:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(29400 + os.getpid() % 500)
+    dist.init_process_group(args.backend, init_method="env://", rank=rank, world_size=world,
+                            device_id=dev if args.backend == "nccl" else None)
+
+    dbatch, dbits, dstoch, unit = MODEL_DEFAULTS[args.model]
+    batch = args.batch or dbatch
+    bits = dbits if args.bits < 0 else args.bits
+    stochastic = dstoch if args.stochastic < 0 else args.stochastic
+    if stochastic:
+        os.environ["CGX_STOCHASTIC_ROUNDING"] = "1"
+
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    is_lm = args.model.startswith("gpt2")
+    if args.model == "resnet50":
+        net = models.resnet50()
+    elif args.model == "resnet18":
+        net = models.resnet18()
+    elif args.model == "gpt2-medium":
+        net = models.gpt2_medium()
+    elif args.model == "gpt2-small":
+        net = models.gpt2_small()
+    elif args.model == "vit-l16":
+        net = models.vit_l16()
+    else:
+        net = models.vit_b16()
+    net = net.to(dev)
+    if not is_lm:
+        net = net.to(memory_format=torch.channels_last)
+    ddp = DDP(net, device_ids=[local_rank], gradient_as_bucket_view=True)
+    if args.backend == "cgx":
+        state = cgx.CGXState(None, layer_min_size=args.layer_min_size,
+                             compression_params={"bits": bits, "bucket_size": args.bucket_size})
+        ddp.register_comm_hook(state, cgx.cgx_hook)
+    if is_lm:
+        opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4, fused=True)
+    else:
+        opt = torch.optim.SGD(ddp.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+
+    # synthetic data of the named shape, in PINNED HOST memory (a few distinct batches, cycled)
+    if is_lm:
+        ds = SyntheticHostDataset.tokens(batch, args.seq_len, net.config.vocab_size, n_batches=4, seed=rank)
+        samples_per_step = batch * args.seq_len
+    else:
+        ds = SyntheticHostDataset.images(batch, 3, 224, 224, 1000, n_batches=4, seed=rank)
+        samples_per_step = batch
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if is_lm:
+                loss = ddp(x, y)
+            else:
+                loss = F.cross_entropy(ddp(x), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def to_dev(b):
+        x, y = b
+        x = x.to(dev, non_blocking=True)
+        y = y.to(dev, non_blocking=True)
+        if not is_lm:
+            x = x.contiguous(memory_format=torch.channels_last)
+        return x, y
+
+    resident = [to_dev(ds[i]) for i in range(len(ds))]
+    torch.cuda.synchronize()
+
+    # ---- warm-up (W >= 3: DDP rebuilds buckets after step 1, layers register at step 3)
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        step(*resident[i % len(resident)])
+    torch.cuda.synchronize()
+    native = cgx.get_backend() if args.backend == "cgx" else None
+
+    def timed(run_one, k):
+        dist.barrier()
+        torch.cuda.synchronize()
+        if native is not None:
+            native.reset_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        last = None
+        for i in range(k):
+            last = run_one(i)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dist.barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        launches = native.stats()[1] if native is not None else 0
+        return t[0].item(), t[1].item(), launches, last
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # (1) device-timed, inputs resident on the device
+    ms_dev, _, launches, last_loss = timed(lambda i: step(*resident[i % len(resident)]), args.steps)
+    # (2) end to end through the public API: pinned host batch -> (prefetch stream) -> step -> loss to host
+    e2e = None
+    if not args.no_e2e:
+        pf = CudaPrefetcher(ds, dev, channels_last=not is_lm)
+        it = iter(pf)
+        for _ in range(2):
+            step(*next(it)).item()
+        def one(i):
+            x, y = next(it)
+            return step(x, y).item()  # D2H read of the loss every step
+        _, ms_wall, _, _ = timed(one, args.steps)
+        e2e_value = samples_per_step * world * args.steps / (ms_wall / 1e3)
+        e2e = {"value": round(e2e_value, 2), "unit": unit, "h2d_bytes_per_step": ds.bytes_per_batch(),
+               "d2h_bytes_per_step": 4, "ms_per_step": round(ms_wall / args.steps, 3),
+               "timing": "host wall clock around K steps incl. prefetch-stream H2D and loss.item(), max over ranks"}
+    clocks = sampler.stop() if rank == 0 else None
+
+    value = samples_per_step * world * args.steps / (ms_dev / 1e3)
+    if rank == 0:
+        tag = f"{bits}bit" if args.backend == "cgx" else "nccl_fp32"
+        out = {
+            "metric": f"{args.model}_ddp_{tag}_{'tokens' if is_lm else 'images'}_per_sec",
+            "value": round(value, 2),
+            "unit": unit,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": warm,
+            "ms_per_step": round(ms_dev / args.steps, 3),
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "bf16",
+            "data": "synthetic (random images/tokens of the named shape, random-init weights)",
+            "impl": args.backend,
+            "config": {
+                "model": args.model, "global_batch": batch * world, "per_gpu_batch": batch,
+                "seq_len": args.seq_len if is_lm else None, "image": None if is_lm else 224,
+                "parallelism": f"dp{world}", "comm": args.backend, "bits": bits if args.backend == "cgx" else 32,
+                "bucket_size": args.bucket_size, "layer_min_size": args.layer_min_size,
+                "stochastic_rounding": bool(stochastic), "fusion_buffer_mb": int(os.environ.get("CGX_FUSION_BUFFER_SIZE_MB", "64")),
+                "optimizer": "AdamW(fused)" if is_lm else "SGD(momentum)", "grad_dtype": "fp32",
+                "l2": "inputs larger than L2: per-step working set (activations+weights+grads) is GBs >> 126 MB L2",
+                "lanes": native.lanes() if native is not None else None,
+            },
+            "gpu_launches": int(launches),
+            "e2e": e2e,
+            "clocks": clocks,
+            "final_loss": round(float(last_loss), 4) if last_loss is not None else None,
+        }
+        print(json.dumps(out), flush=True)
+    dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

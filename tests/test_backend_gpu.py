@@ -1,0 +1,152 @@
+"""The `cgx` backend on CUDA tensors: one process per rank. With >= 2 GPUs each
+rank gets its own device and the full reference test-suite
+(/root/reference/test/test_cgx.py) runs, plus DDP + cgx_hook. With a single GPU
+only the world_size == 1 path is exercised here (the multi-rank protocol is
+covered by the single-process virtual-rank tests in test_kernels_gpu.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+
+from _dist_utils import spawn
+
+pytestmark = pytest.mark.gpu
+
+
+def _world1(rank, world):
+    import torch_cgx_b200 as cgx
+
+    torch.cuda.set_device(0)
+    dist.init_process_group("cgx", init_method="env://", rank=rank, world_size=world)
+    try:
+        os.environ["CGX_COMPRESSION_QUANTIZATION_BITS"] = "4"
+        x = torch.randn(100_000, device="cuda")
+        ref = cgx.ops.fake_quantize(x.cpu(), 4, 512)
+        y = x.clone()
+        dist.all_reduce(y)
+        torch.cuda.synchronize()
+        # world 1: the owner's requantize + self-decode is all that happens
+        assert torch.equal(y.cpu(), ref)
+        be = cgx.get_backend()
+        assert be is not None and be.p2p_ready() and be.stats()[1] >= 1
+        os.environ["CGX_COMPRESSION_QUANTIZATION_BITS"] = "32"
+        z = x.clone()
+        dist.all_reduce(z)
+        assert torch.equal(z, x)
+        t = torch.tensor([3], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t)  # NCCL delegate
+        assert t.item() == 3
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_backend_world1():
+    spawn(_world1, 1)
+
+
+def _reference_suite(rank, world):
+    import torch_cgx  # noqa: F401
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("cgx", init_method="env://", rank=rank, world_size=world)
+    try:
+        dev = torch.device("cuda", rank)
+        # test_compressed_exact
+        for q in (2, 4, 8):
+            os.environ["CGX_COMPRESSION_QUANTIZATION_BITS"] = str(q)
+            for dtype in (torch.float16, torch.float32, torch.int32):
+                for n in (1, 2, 8, 128, 1024, 1_000_000):
+                    for _ in range(3):
+                        t = torch.tensor([rank + 1] * n, dtype=dtype, device=dev)
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                        exp = torch.tensor([world * (world + 1) // 2] * n, dtype=dtype, device=dev)
+                        assert torch.equal(t, exp), f"bits {q} dtype {dtype} n {n}"
+        # test_compressed_non_exact
+        for q in (2, 3, 4, 6, 8):
+            os.environ["CGX_COMPRESSION_QUANTIZATION_BITS"] = str(q)
+            for dtype in (torch.float16, torch.float32):
+                for n in (128, 1024, 1025, 16_384, 1_000_000):
+                    ar = np.arange(-n / 2, n / 2, 1.0)
+                    if dtype == torch.float16:
+                        ar = ar * 1e-3
+                    for bucket in (64, 512, 2048):
+                        os.environ["CGX_COMPRESSION_BUCKET_SIZE"] = str(bucket)
+                        t = torch.tensor((rank + 1) * ar, dtype=dtype, device=dev)
+                        exp = torch.tensor((world * (world + 1) / 2) * ar, dtype=dtype, device=dev)
+                        dist.all_reduce(t)
+                        err = torch.norm((t - exp).float(), p=float("inf")).item()
+                        assert err < 2 * min(bucket, n) / ((1 << q) - 1) * world * (world + 1)
+                        # replicas are bit-identical
+                        g = [torch.empty_like(t) for _ in range(world)]
+                        dist.all_gather(g, t)
+                        assert all(torch.equal(g[0], gi) for gi in g)
+        # test_uncompressed
+        os.environ["CGX_COMPRESSION_QUANTIZATION_BITS"] = "32"
+        for dtype in (torch.float16, torch.float32, torch.bfloat16, torch.int32):
+            for n in (1, 8, 1024, 1_000_000):
+                t = torch.tensor([rank + 1] * n, dtype=dtype, device=dev)
+                dist.all_reduce(t)
+                assert torch.equal(t, torch.tensor([world * (world + 1) // 2] * n, dtype=dtype, device=dev))
+        # AVG is fused into the kernel
+        t = torch.full((10_000,), float(rank + 1), device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        assert torch.allclose(t, torch.full_like(t, (world + 1) / 2))
+        # async work + future
+        t = torch.ones(1 << 20, device=dev)
+        w = dist.all_reduce(t, async_op=True)
+        w.wait()
+        assert torch.equal(t, torch.full_like(t, float(world)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.multigpu
+def test_reference_suite_two_gpus():
+    spawn(_reference_suite, 2, timeout=600)
+
+
+def _ddp_gpu(rank, world):
+    import torch_cgx_b200 as cgx
+    from cgx_utils import CGXState, cgx_hook
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("cgx", init_method="env://", rank=rank, world_size=world)
+    try:
+        from torch_cgx_b200.models import resnet18
+
+        torch.manual_seed(0)
+        model = resnet18(num_classes=10, cifar_stem=True).cuda()
+        ddp = DDP(model, device_ids=[rank])
+        state = CGXState(None, layer_min_size=1024, compression_params={"bits": 4, "bucket_size": 512})
+        ddp.register_comm_hook(state, cgx_hook)
+        opt = torch.optim.SGD(ddp.parameters(), lr=0.05, momentum=0.9)
+        losses = []
+        torch.manual_seed(1234 + rank)
+        x = torch.randn(32, 3, 32, 32, device="cuda")
+        y = torch.randint(0, 10, (32,), device="cuda")
+        for step in range(12):
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.cross_entropy(ddp(x), y)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        assert losses[-1] < losses[0], losses  # it learns (memorises the fixed batch) through 4-bit gradients
+        be = cgx.get_backend()
+        assert be.stats()[1] > 0 and be.stats()[3] < be.stats()[4]  # compressed bytes < raw bytes
+        flat = torch.cat([p.detach().reshape(-1) for p in ddp.parameters()])
+        g = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(g, flat)
+        assert all(torch.equal(g[0], gi) for gi in g)  # replicas bit-identical
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.multigpu
+def test_ddp_hook_two_gpus():
+    spawn(_ddp_gpu, 2, timeout=600)

@@ -29,6 +29,7 @@ from .backend import (  # noqa: E402
 )
 from .parallel.hooks import CGXState, cgx_hook  # noqa: E402
 from .utils.launch import map_launcher_env  # noqa: E402
+from . import models, ops, utils  # noqa: E402,F401
 
 register_backend()
 
