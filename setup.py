@@ -39,6 +39,15 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
 ]
 CXX_FLAGS = ["-O3", "-std=c++17", "-ffp-contract=off", "-Wno-unused-function"]
+# This image's default compiler wrapper (/opt/gcc/bin/g++) finds only a *static*
+# libstdc++ (its libstdc++.so symlink dangles); a private static copy inside a
+# Python extension has uninitialised locale state and segfaults on the first
+# ostream insertion. Always link the system's shared libstdc++ explicitly.
+LINK_FLAGS = []
+for _d in ("/usr/lib/x86_64-linux-gnu", "/lib/x86_64-linux-gnu"):
+    if (Path(_d) / "libstdc++.so.6").exists():
+        LINK_FLAGS = [f"-L{_d}", "-l:libstdc++.so.6"]
+        break
 
 os.environ.setdefault("MAX_JOBS", str(os.cpu_count() or 4))
 
@@ -52,6 +61,7 @@ setup(
             name="torch_cgx_b200._C",
             sources=[str(CSRC / s) for s in SOURCES],
             extra_compile_args={"cxx": CXX_FLAGS, "nvcc": NVCC_FLAGS},
+            extra_link_args=LINK_FLAGS,
         )
     ],
     cmdclass={"build_ext": BuildExtension.with_options(use_ninja=True, no_python_abi_suffix=False)},

@@ -46,7 +46,7 @@ const DevicePlan* FusedSra::prepare(const std::vector<LayerSpec>& layers, int dt
       cuda_check(cudaMemcpyAsync(dp->d_lane_first, dp->plan.lane_first.data(), lb, cudaMemcpyHostToDevice, stream),
                  "upload plan lanes");
     }
-    log_msg(2, "cgx[%d]: new plan %s", rank(), describe_plan(dp->plan).c_str());
+    if (log_level() >= 2) log_msg(2, "cgx[%d]: new plan %s", rank(), describe_plan(dp->plan).c_str());
     it = cache_.emplace(key, std::move(dp)).first;
   }
   const DevicePlan* dp = it->second.get();
