@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Compressed-allreduce bandwidth sweep (BASELINE.json configs[4]): message sizes
+1 KB - 1 GB x bits {2,4,8,32} on N GPUs, cgx fused P2P kernel vs stock NCCL
+ncclAllReduce on the same box.  Device-timed per iteration with CUDA events on
+the launching stream, L2 flushed between iterations, MAX over ranks, median of
+iterations.
+
+  torchrun --nproc-per-node N bench/allreduce_sweep.py --out gpurun_out/sweep_N.json
+
+Reported per row:
+  time_us        median device time of one allreduce (max over ranks)
+  algbw_gbs      message bytes / time
+  busbw_gbs      algbw * 2(W-1)/W          (NCCL's "bus bandwidth" of the *uncompressed* message)
+  wire_gbs       bytes this rank actually pushed over NVLink / time (packed bytes, per direction)
+  speedup_vs_nccl
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import torch_cgx_b200 as cgx  # noqa: E402
+
+
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
+def time_allreduce(fn, flush, iters, warmup, dev):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    t = torch.tensor(ts, device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks, per iteration
+    return median(t.tolist())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/sweep.json")
+    ap.add_argument("--min-kb", type=int, default=1)
+    ap.add_argument("--max-mb", type=int, default=1024)
+    ap.add_argument("--bits", default="2,4,8,32")
+    ap.add_argument("--dtype", default="float32")
+    ap.add_argument("--iters", type=int, default=15)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--bucket-size", type=int, default=512)
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+
+    rank, world, local = cgx.map_launcher_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("cgx", init_method="env://", rank=rank, world_size=world)
+    nccl = dist.new_group(backend="nccl")
+    dtype = getattr(torch, args.dtype)
+    es = torch.empty((), dtype=dtype).element_size()
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    os.environ["CGX_COMPRESSION_BUCKET_SIZE"] = str(args.bucket_size)
+    be = cgx.get_backend()
+
+    sizes = []
+    s = args.min_kb << 10
+    while s <= (args.max_mb << 20):
+        sizes.append(s)
+        s *= 4
+    rows = []
+    for nbytes in sizes:
+        n = nbytes // es
+        x = torch.randn(n, device=dev).to(dtype)
+        iters = args.iters if nbytes <= (256 << 20) else max(5, args.iters // 3)
+        t_nccl = time_allreduce(lambda: dist.all_reduce(x, group=nccl), flush, iters, args.warmup, dev)
+        row_base = {"bytes": nbytes, "dtype": args.dtype, "world": world}
+        r = dict(row_base, impl="nccl", bits=32, time_us=round(t_nccl, 2),
+                 algbw_gbs=round(nbytes / t_nccl / 1e3, 2), busbw_gbs=round(nbytes / t_nccl / 1e3 * 2 * (world - 1) / world, 2))
+        rows.append(r)
+        if rank == 0:
+            print(json.dumps(r), flush=True)
+        for bits in [int(b) for b in args.bits.split(",")]:
+            os.environ["CGX_COMPRESSION_QUANTIZATION_BITS"] = str(bits)
+            x.normal_()
+            be.reset_stats()
+            t = time_allreduce(lambda: dist.all_reduce(x), flush, iters, args.warmup, dev)
+            st = be.stats()
+            wire_per_call = st[3] / max(1, st[0])
+            r = dict(row_base, impl="cgx", bits=bits, time_us=round(t, 2), algbw_gbs=round(nbytes / t / 1e3, 2),
+                     busbw_gbs=round(nbytes / t / 1e3 * 2 * (world - 1) / world, 2),
+                     wire_bytes_per_rank=int(wire_per_call), wire_gbs=round(wire_per_call / t / 1e3, 2),
+                     kernel_launches_per_call=round(st[1] / max(1, st[0]), 2),
+                     speedup_vs_nccl=round(t_nccl / t, 3))
+            rows.append(r)
+            if rank == 0:
+                print(json.dumps(r), flush=True)
+        del x
+    if rank == 0:
+        Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+        Path(args.out).write_text(json.dumps({"world": world, "lanes": be.lanes(), "rows": rows,
+                                              "timing": "CUDA events per iteration, L2 flushed, max over ranks, median"}, indent=1))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
