@@ -29,6 +29,7 @@ struct SraParams {
   uint32_t* flags2[kMaxPeers];
   uint32_t* status;              // local error word (0 = ok)
   uint64_t timeout_ns;
+  int variant;                   // 0 = warp-centric kernel (default), 1 = CTA/shared-memory kernel (v1)
 };
 
 constexpr int kSraThreads = 512;

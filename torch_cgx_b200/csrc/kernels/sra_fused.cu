@@ -24,6 +24,7 @@
 // (scatter_reduce_allgather.cc:308-413, allreduce_hooks.py:48-59).
 #include "block_device.cuh"
 #include "launch.h"
+#include "warp_path.cuh"
 
 namespace cgx {
 using namespace dev;
@@ -145,6 +146,282 @@ __global__ void __launch_bounds__(kSraThreads, 2) sra_fused_kernel(const SraPara
   }
 }
 
+
+// ===========================================================================
+// v2: warp-centric kernel. Same protocol and bit-identical results, but the
+// unit of scheduling is a warp "item" (one quantization bucket, or 2048 raw
+// elements): items of a lane are dealt round-robin to the CTA's warps, which
+// run without any block-wide barrier; chunk completion is tracked with
+// shared-memory counters and published by whichever warp finishes last.
+// ===========================================================================
+template <typename T>
+__global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const SraParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Tile& tile = *reinterpret_cast<Tile*>(smem_raw);
+  __shared__ uint32_t s_expect[kMaxPeers];
+  __shared__ uint32_t s_done_a[kMaxPeers];
+  __shared__ uint32_t s_done_b;
+  __shared__ int s_abort;
+
+  const int lane = blockIdx.x;
+  const int r = p.rank, W = p.world, G = p.lanes;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t warp = tid >> 5, wl = tid & 31u, nwarps = blockDim.x >> 5;
+  T* data = reinterpret_cast<T*>(p.data);
+
+  if (tid < (uint32_t)W) {
+    uint32_t tot = 0;
+    for (uint32_t b = p.lane_first[tid * G + lane]; b < p.lane_first[tid * G + lane + 1]; ++b)
+      tot += block_items(p.blocks[b]);
+    s_expect[tid] = tot;
+    s_done_a[tid] = 0;
+  }
+  if (tid == 0) {
+    s_done_b = 0;
+    s_abort = 0;
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase A
+  {
+    RngKey rng = p.rng;
+    rng.stream = (uint32_t)r * 2u;
+    uint32_t it = 0;
+    for (int s = 1; s < W; ++s) {
+      const int dstp = (r + s) % W;
+      const uint32_t b0 = p.lane_first[dstp * G + lane], b1 = p.lane_first[dstp * G + lane + 1];
+      if (b0 == b1) continue;
+      uint8_t* slot = p.recv1[dstp] + (size_t)r * p.slot_bytes;
+      uint32_t* flag = p.flags1[dstp] + (size_t)r * p.flag_stride + lane;
+      const uint32_t expect = s_expect[dstp];
+      for (uint32_t b = b0; b < b1; ++b) {
+        const BlockDesc d = p.blocks[b];
+        uint8_t* rec = slot + d.wire_off;
+        const uint32_t n = block_n(d);
+        const int bits = block_bits(d);
+        const T* blk = data + d.elem_off;
+        const bool aligned = (reinterpret_cast<uintptr_t>(blk) & 15u) == 0;
+        if (block_is_raw(d)) {
+          const uint32_t ni = div_up(n, kRawItemElems);
+          for (uint32_t i = 0; i < ni; ++i) {
+            if ((it++) % nwarps != warp) continue;
+            warp_send_raw<T>(blk, aligned, n, i, p.prescale, rec);
+            __syncwarp();
+            if (wl == 0 && atom_add_acq_rel_cta(&s_done_a[dstp], 1u) + 1u == expect) st_release_sys(flag, p.epoch);
+          }
+        } else if (block_is_fast(d)) {
+          const uint32_t nb = block_num_buckets(n, d.bucket);
+          const uint32_t meta_bytes = block_meta_bytes(n, d.bucket);
+          for (uint32_t bk = 0; bk < nb; ++bk) {
+            if ((it++) % nwarps != warp) continue;
+            const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
+            float x[kMaxGpl][8];
+            float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+            BucketCtx c;
+            for (uint32_t sl = 0; sl < ns; ++sl) {
+              c = make_slice_ctx(d, bk, sl);
+              warp_load_bucket<T>(blk, aligned, c, p.prescale, x);
+              warp_minmax_update(x, c, mn, mx);
+            }
+            const BucketMeta m = warp_minmax_finish(mn, mx, bits);
+            warp_store_meta(m, bk, &rec, 1);
+            if (ns == 1) {
+              warp_quantize_store<T, false>(x, c, m, bits, bk, meta_bytes, rng, b, &rec, 1, nullptr, false);
+            } else {
+              for (uint32_t sl = 0; sl < ns; ++sl) {
+                c = make_slice_ctx(d, bk, sl);
+                warp_load_bucket<T>(blk, aligned, c, p.prescale, x);
+                warp_quantize_store<T, false>(x, c, m, bits, bk, meta_bytes, rng, b, &rec, 1, nullptr, false);
+              }
+            }
+            __syncwarp();
+            if (wl == 0 && atom_add_acq_rel_cta(&s_done_a[dstp], 1u) + 1u == expect) st_release_sys(flag, p.epoch);
+          }
+        } else {
+          load_block<T>(data, d, p.prescale, tile.acc);
+          __syncthreads();
+          compute_meta(tile.acc, n, d.bucket, bits, tile.meta, tile.inv);
+          __syncthreads();
+          pack_block<T, false>(tile.acc, d, tile.meta, tile.inv, tile.pay, rng, b, nullptr);
+          __syncthreads();
+          store_record(tile.meta, tile.pay, block_meta_bytes(n, d.bucket), block_payload_bytes(n, bits), &rec, 1);
+          __syncthreads();
+          if (tid == 0 && atom_add_acq_rel_cta(&s_done_a[dstp], 1u) + 1u == expect) st_release_sys(flag, p.epoch);
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ phase B
+  {
+    const uint32_t b0 = p.lane_first[r * G + lane], b1 = p.lane_first[r * G + lane + 1];
+    if (b1 > b0) {
+      bool ok = true;
+      if (wl < (uint32_t)W && (int)wl != r) {
+        ok = wait_flag(p.flags1[r] + (size_t)wl * p.flag_stride + lane, p.epoch, p.timeout_ns);
+        if (!ok) {
+          s_abort = 1;
+          *p.status = kSraTimeoutPhase1 | (wl << 8) | ((uint32_t)lane << 16);
+        }
+      }
+      if (!__all_sync(0xffffffffu, ok)) return;
+
+      RngKey rng = p.rng;
+      rng.stream = (uint32_t)r * 2u + 1u;
+      const uint32_t expect = s_expect[r];
+      const uint8_t* src_rec[kMaxPeers];
+      uint8_t* dst_rec[kMaxPeers];
+      uint32_t it = 0;
+      for (uint32_t b = b0; b < b1; ++b) {
+        const BlockDesc d = p.blocks[b];
+        int np = 0;
+        for (int q = 0; q < W; ++q) {
+          if (q == r) continue;
+          src_rec[np] = p.recv1[r] + (size_t)q * p.slot_bytes + d.wire_off;
+          dst_rec[np] = p.recv2[q] + (size_t)r * p.slot_bytes + d.wire_off;
+          ++np;
+        }
+        const uint32_t n = block_n(d);
+        const int bits = block_bits(d);
+        T* blk = data + d.elem_off;
+        const bool aligned = (reinterpret_cast<uintptr_t>(blk) & 15u) == 0;
+        bool finished = false;  // did this warp/thread complete the chunk?
+        if (block_is_raw(d)) {
+          const uint32_t ni = div_up(n, kRawItemElems);
+          for (uint32_t i = 0; i < ni; ++i) {
+            if ((it++) % nwarps != warp) continue;
+            warp_reduce_raw<T>(blk, aligned, n, i, p.prescale, src_rec, np, dst_rec, np);
+            __syncwarp();
+            uint32_t last = 0;
+            if (wl == 0) last = (atom_add_acq_rel_cta(&s_done_b, 1u) + 1u == expect) ? 1u : 0u;
+            finished |= __shfl_sync(0xffffffffu, last, 0) != 0;
+          }
+        } else if (block_is_fast(d)) {
+          const uint32_t nb = block_num_buckets(n, d.bucket);
+          const uint32_t meta_bytes = block_meta_bytes(n, d.bucket);
+          for (uint32_t bk = 0; bk < nb; ++bk) {
+            if ((it++) % nwarps != warp) continue;
+            const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
+            float x[kMaxGpl][8];
+            BucketCtx c;
+            // own slice + the W-1 decoded peer copies, summed in fixed rank order
+            auto gather = [&](uint32_t sl) {
+              c = make_slice_ctx(d, bk, sl);
+              warp_load_bucket<T>(blk, aligned, c, p.prescale, x);
+              // peers in batches of 4: all loads of a batch are issued before any is consumed
+              for (int q0 = 0; q0 < np; q0 += 4) {
+                uint64_t w[4][kMaxGpl];
+                BucketMeta pm[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (q0 + u < np) warp_fetch_peer(src_rec[q0 + u], meta_bytes, bk, bits, c, w[u], pm[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (q0 + u < np) warp_accumulate(w[u], pm[u], bits, c, x);
+              }
+            };
+            float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+            for (uint32_t sl = 0; sl < ns; ++sl) {
+              gather(sl);
+              warp_minmax_update(x, c, mn, mx);
+            }
+            const BucketMeta m = warp_minmax_finish(mn, mx, bits);
+            warp_store_meta(m, bk, dst_rec, np);
+            if (ns == 1) {
+              warp_quantize_store<T, true>(x, c, m, bits, bk, meta_bytes, rng, b, dst_rec, np, blk, aligned);
+            } else {
+              // NB: the self-decode of slice sl overwrites only slice sl of my own gradient, which
+              // later slices never re-read
+              for (uint32_t sl = 0; sl < ns; ++sl) {
+                gather(sl);
+                warp_quantize_store<T, true>(x, c, m, bits, bk, meta_bytes, rng, b, dst_rec, np, blk, aligned);
+              }
+            }
+            __syncwarp();
+            uint32_t last = 0;
+            if (wl == 0) last = (atom_add_acq_rel_cta(&s_done_b, 1u) + 1u == expect) ? 1u : 0u;
+            finished |= __shfl_sync(0xffffffffu, last, 0) != 0;
+          }
+        } else {
+          load_block<T>(data, d, p.prescale, tile.acc);
+          __syncthreads();
+          for (int k = 0; k < np; ++k) decode_add<T>(src_rec[k], d, tile.acc);
+          __syncthreads();
+          compute_meta(tile.acc, n, d.bucket, bits, tile.meta, tile.inv);
+          __syncthreads();
+          pack_block<T, true>(tile.acc, d, tile.meta, tile.inv, tile.pay, rng, b, data);
+          __syncthreads();
+          store_record(tile.meta, tile.pay, block_meta_bytes(n, d.bucket), block_payload_bytes(n, bits), dst_rec, np);
+          __syncthreads();
+          uint32_t last = 0;
+          if (tid == 0) last = (atom_add_acq_rel_cta(&s_done_b, 1u) + 1u == expect) ? 1u : 0u;
+          if (warp == 0) finished |= __shfl_sync(0xffffffffu, last, 0) != 0;
+        }
+        if (finished && wl < (uint32_t)W && (int)wl != r)
+          st_release_sys(p.flags2[wl] + (size_t)r * p.flag_stride + lane, p.epoch);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ phase C
+  {
+    uint32_t it = 0;
+    for (int s = 1; s < W; ++s) {
+      const int q = (r + s) % W;
+      const uint32_t b0 = p.lane_first[q * G + lane], b1 = p.lane_first[q * G + lane + 1];
+      if (b0 == b1) continue;
+      const uint32_t* flag = p.flags2[r] + (size_t)q * p.flag_stride + lane;
+      const uint8_t* slot = p.recv2[r] + (size_t)q * p.slot_bytes;
+      bool waited = false;
+      auto ensure = [&]() -> bool {
+        if (waited) return true;
+        uint32_t ok = 1;
+        if (wl == 0) {
+          ok = wait_flag(flag, p.epoch, p.timeout_ns) ? 1u : 0u;
+          if (!ok) {
+            s_abort = 1;
+            *p.status = kSraTimeoutPhase2 | ((uint32_t)q << 8) | ((uint32_t)lane << 16);
+          }
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        waited = true;
+        return ok != 0;
+      };
+      for (uint32_t b = b0; b < b1; ++b) {
+        const BlockDesc d = p.blocks[b];
+        const uint8_t* rec = slot + d.wire_off;
+        const uint32_t n = block_n(d);
+        const int bits = block_bits(d);
+        T* blk = data + d.elem_off;
+        const bool aligned = (reinterpret_cast<uintptr_t>(blk) & 15u) == 0;
+        if (block_is_raw(d)) {
+          const uint32_t ni = div_up(n, kRawItemElems);
+          for (uint32_t i = 0; i < ni; ++i) {
+            if ((it++) % nwarps != warp) continue;
+            if (!ensure()) return;
+            warp_copy_raw<T>(rec, blk, aligned, n, i);
+          }
+        } else if (block_is_fast(d)) {
+          const uint32_t nb = block_num_buckets(n, d.bucket);
+          const uint32_t meta_bytes = block_meta_bytes(n, d.bucket);
+          for (uint32_t bk = 0; bk < nb; ++bk) {
+            if ((it++) % nwarps != warp) continue;
+            if (!ensure()) return;
+            const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
+            for (uint32_t sl = 0; sl < ns; ++sl) {
+              const BucketCtx c = make_slice_ctx(d, bk, sl);
+              warp_decode_store<T>(rec, meta_bytes, bk, bits, c, blk, aligned);
+            }
+          }
+        } else {
+          if (!ensure()) return;
+          decode_store<T>(rec, d, data);
+        }
+      }
+    }
+  }
+}
+
 template <typename T>
 cudaError_t launch_t(const SraParams& p, cudaStream_t stream) {
   static bool configured[64] = {};
@@ -154,9 +431,15 @@ cudaError_t launch_t(const SraParams& p, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(sra_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(Tile));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sra_fused_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(Tile));
+    if (e != cudaSuccess) return e;
     configured[dev & 63] = true;
   }
-  sra_fused_kernel<T><<<p.lanes, kSraThreads, sizeof(Tile), stream>>>(p);
+  if (p.variant == 1)
+    sra_fused_kernel<T><<<p.lanes, kSraThreads, sizeof(Tile), stream>>>(p);
+  else
+    sra_fused_warp_kernel<T><<<p.lanes, kSraThreads, sizeof(Tile), stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -166,10 +449,14 @@ int max_resident_t() {
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaFuncSetAttribute(sra_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile));
+  cudaFuncSetAttribute(sra_fused_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile));
+  int per_sm2 = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sra_fused_kernel<T>, kSraThreads, sizeof(Tile)) !=
-      cudaSuccess)
+          cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, sra_fused_warp_kernel<T>, kSraThreads,
+                                                    sizeof(Tile)) != cudaSuccess)
     return 0;
-  return sms * per_sm;
+  return sms * (per_sm < per_sm2 ? per_sm : per_sm2);
 }
 
 }  // namespace

@@ -11,6 +11,7 @@ namespace cgx {
 FusedSra::FusedSra(SymmetricHeap* heap, int max_lanes, int64_t timeout_ms, uint32_t min_lane_elems)
     : heap_(heap), max_lanes_(max_lanes), timeout_ns_((uint64_t)timeout_ms * 1000000ull),
       min_lane_elems_(min_lane_elems) {
+  variant_ = env_str("CGX_KERNEL", "warp") == "block" ? 1 : 0;
   if (max_lanes_ < 1) max_lanes_ = 1;
   if ((uint32_t)max_lanes_ > heap_->layout().flag_stride) max_lanes_ = (int)heap_->layout().flag_stride;
 }
@@ -80,6 +81,7 @@ void FusedSra::run(const DevicePlan& dp, void* data, float prescale, const RngPa
   }
   p.status = heap_->status_device();
   p.timeout_ns = timeout_ns_;
+  p.variant = variant_;
   cuda_check(launch_sra_fused(p, stream), "launch_sra_fused");
   ++launches_;
 }

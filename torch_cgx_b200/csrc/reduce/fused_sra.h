@@ -54,6 +54,7 @@ class FusedSra {
   uint32_t min_lane_elems_;
   uint32_t epoch_ = 0;
   uint64_t launches_ = 0;
+  int variant_ = 0;
   std::unordered_map<uint64_t, std::unique_ptr<DevicePlan>> cache_;
 };
 
