@@ -154,6 +154,106 @@ __global__ void __launch_bounds__(kSraThreads, 2) sra_fused_kernel(const SraPara
 // run without any block-wide barrier; chunk completion is tracked with
 // shared-memory counters and published by whichever warp finishes last.
 // ===========================================================================
+constexpr uint32_t kNumWarps = kSraThreads / 32;
+constexpr int kPeerBatch = 2;  // peers whose packed words are in flight together (register budget)
+#define CGX_INF_POS __int_as_float(0x7f800000)
+#define CGX_INF_NEG __int_as_float(0xff800000)
+
+// phase A: my copy of one bucket of a peer's chunk -> quantize -> peer's slot
+template <typename T, bool FULL>
+__device__ __forceinline__ void bucket_send(const T* __restrict__ blk, bool aligned, const BlockDesc& d, uint32_t bk,
+                                            float prescale, const RngKey& rng, uint32_t b, uint8_t* rec) {
+  const int bits = block_bits(d);
+  const uint32_t meta_bytes = block_meta_bytes(block_n(d), d.bucket);
+  const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
+  float x[kMaxGpl][8];
+  float mn = CGX_INF_POS, mx = CGX_INF_NEG;
+  BucketCtx c;
+  for (uint32_t sl = 0; sl < ns; ++sl) {
+    c = make_slice_ctx(d, bk, sl);
+    warp_load_bucket<T, FULL>(blk, aligned, c, prescale, x);
+    warp_minmax_update<FULL>(x, c, mn, mx);
+  }
+  const BucketMeta m = warp_minmax_finish(mn, mx, bits);
+  warp_store_meta(m, bk, &rec, 1);
+  if (ns == 1) {
+    warp_quantize_store<T, false, FULL>(x, c, m, bits, meta_bytes, rng, b, &rec, 1, nullptr, false);
+  } else {
+    for (uint32_t sl = 0; sl < ns; ++sl) {
+      c = make_slice_ctx(d, bk, sl);
+      warp_load_bucket<T, FULL>(blk, aligned, c, prescale, x);
+      warp_quantize_store<T, false, FULL>(x, c, m, bits, meta_bytes, rng, b, &rec, 1, nullptr, false);
+    }
+  }
+}
+
+// own slice + the W-1 decoded peer copies, summed in fixed rank order
+template <typename T, bool FULL>
+__device__ __forceinline__ void slice_gather(T* __restrict__ blk, bool aligned, const BlockDesc& d, uint32_t bk,
+                                             uint32_t sl, float prescale, uint32_t meta_bytes, int bits,
+                                             const uint8_t* const* src_rec, int np, BucketCtx& c,
+                                             float (&x)[kMaxGpl][8]) {
+  c = make_slice_ctx(d, bk, sl);
+  warp_load_bucket<T, FULL>(blk, aligned, c, prescale, x);
+  // peers in batches: all loads of a batch are issued before any is consumed
+  for (int q0 = 0; q0 < np; q0 += kPeerBatch) {
+    uint64_t w[kPeerBatch][kMaxGpl];
+    BucketMeta pm[kPeerBatch];
+#pragma unroll
+    for (int u = 0; u < kPeerBatch; ++u)
+      if (q0 + u < np) warp_fetch_peer<FULL>(src_rec[q0 + u], meta_bytes, bk, bits, c, w[u], pm[u]);
+#pragma unroll
+    for (int u = 0; u < kPeerBatch; ++u)
+      if (q0 + u < np) warp_accumulate<FULL>(w[u], pm[u], bits, c, x);
+  }
+}
+
+// phase B: reduce one bucket of MY chunk, requantize, publish to every peer, self-decode
+template <typename T, bool FULL>
+__device__ __forceinline__ void bucket_reduce(T* __restrict__ blk, bool aligned, const BlockDesc& d, uint32_t bk,
+                                              float prescale, const RngKey& rng, uint32_t b,
+                                              const uint8_t* const* src_rec, uint8_t* const* dst_rec, int np) {
+  const int bits = block_bits(d);
+  const uint32_t meta_bytes = block_meta_bytes(block_n(d), d.bucket);
+  const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
+  float x[kMaxGpl][8];
+  float mn = CGX_INF_POS, mx = CGX_INF_NEG;
+  BucketCtx c;
+  for (uint32_t sl = 0; sl < ns; ++sl) {
+    slice_gather<T, FULL>(blk, aligned, d, bk, sl, prescale, meta_bytes, bits, src_rec, np, c, x);
+    warp_minmax_update<FULL>(x, c, mn, mx);
+  }
+  const BucketMeta m = warp_minmax_finish(mn, mx, bits);
+  warp_store_meta(m, bk, dst_rec, np);
+  if (ns == 1) {
+    warp_quantize_store<T, true, FULL>(x, c, m, bits, meta_bytes, rng, b, dst_rec, np, blk, aligned);
+  } else {
+    // the self-decode of slice sl overwrites only slice sl of my own gradient, which later
+    // slices never re-read
+    for (uint32_t sl = 0; sl < ns; ++sl) {
+      slice_gather<T, FULL>(blk, aligned, d, bk, sl, prescale, meta_bytes, bits, src_rec, np, c, x);
+      warp_quantize_store<T, true, FULL>(x, c, m, bits, meta_bytes, rng, b, dst_rec, np, blk, aligned);
+    }
+  }
+}
+
+// phase C: a peer's reduced bucket -> my gradient buffer
+template <typename T, bool FULL>
+__device__ __forceinline__ void bucket_recv(const uint8_t* rec, T* __restrict__ blk, bool aligned, const BlockDesc& d,
+                                            uint32_t bk) {
+  const int bits = block_bits(d);
+  const uint32_t meta_bytes = block_meta_bytes(block_n(d), d.bucket);
+  const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
+  for (uint32_t sl = 0; sl < ns; ++sl) {
+    const BucketCtx c = make_slice_ctx(d, bk, sl);
+    warp_decode_store<T, FULL>(rec, meta_bytes, bk, bits, c, blk, aligned);
+  }
+}
+
+__device__ __forceinline__ bool bucket_is_full(const BlockDesc& d, uint32_t bk, bool aligned) {
+  return aligned && (bucket_count(d, bk) % kSliceElems) == 0;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const SraParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -166,7 +266,7 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const Sr
   const int lane = blockIdx.x;
   const int r = p.rank, W = p.world, G = p.lanes;
   const uint32_t tid = threadIdx.x;
-  const uint32_t warp = tid >> 5, wl = tid & 31u, nwarps = blockDim.x >> 5;
+  const uint32_t warp = tid >> 5, wl = tid & 31u;
   T* data = reinterpret_cast<T*>(p.data);
 
   if (tid < (uint32_t)W) {
@@ -186,7 +286,7 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const Sr
   {
     RngKey rng = p.rng;
     rng.stream = (uint32_t)r * 2u;
-    uint32_t it = 0;
+    uint32_t base = 0;  // items dealt so far: item i goes to warp (i % kNumWarps)
     for (int s = 1; s < W; ++s) {
       const int dstp = (r + s) % W;
       const uint32_t b0 = p.lane_first[dstp * G + lane], b1 = p.lane_first[dstp * G + lane + 1];
@@ -198,46 +298,30 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const Sr
         const BlockDesc d = p.blocks[b];
         uint8_t* rec = slot + d.wire_off;
         const uint32_t n = block_n(d);
-        const int bits = block_bits(d);
         const T* blk = data + d.elem_off;
         const bool aligned = (reinterpret_cast<uintptr_t>(blk) & 15u) == 0;
+        const uint32_t first = (warp - base) & (kNumWarps - 1);
         if (block_is_raw(d)) {
           const uint32_t ni = div_up(n, kRawItemElems);
-          for (uint32_t i = 0; i < ni; ++i) {
-            if ((it++) % nwarps != warp) continue;
+          for (uint32_t i = first; i < ni; i += kNumWarps) {
             warp_send_raw<T>(blk, aligned, n, i, p.prescale, rec);
             __syncwarp();
             if (wl == 0 && atom_add_acq_rel_cta(&s_done_a[dstp], 1u) + 1u == expect) st_release_sys(flag, p.epoch);
           }
+          base += ni;
         } else if (block_is_fast(d)) {
           const uint32_t nb = block_num_buckets(n, d.bucket);
-          const uint32_t meta_bytes = block_meta_bytes(n, d.bucket);
-          for (uint32_t bk = 0; bk < nb; ++bk) {
-            if ((it++) % nwarps != warp) continue;
-            const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
-            float x[kMaxGpl][8];
-            float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-            BucketCtx c;
-            for (uint32_t sl = 0; sl < ns; ++sl) {
-              c = make_slice_ctx(d, bk, sl);
-              warp_load_bucket<T>(blk, aligned, c, p.prescale, x);
-              warp_minmax_update(x, c, mn, mx);
-            }
-            const BucketMeta m = warp_minmax_finish(mn, mx, bits);
-            warp_store_meta(m, bk, &rec, 1);
-            if (ns == 1) {
-              warp_quantize_store<T, false>(x, c, m, bits, bk, meta_bytes, rng, b, &rec, 1, nullptr, false);
-            } else {
-              for (uint32_t sl = 0; sl < ns; ++sl) {
-                c = make_slice_ctx(d, bk, sl);
-                warp_load_bucket<T>(blk, aligned, c, p.prescale, x);
-                warp_quantize_store<T, false>(x, c, m, bits, bk, meta_bytes, rng, b, &rec, 1, nullptr, false);
-              }
-            }
+          for (uint32_t bk = first; bk < nb; bk += kNumWarps) {
+            if (bucket_is_full(d, bk, aligned))
+              bucket_send<T, true>(blk, aligned, d, bk, p.prescale, rng, b, rec);
+            else
+              bucket_send<T, false>(blk, aligned, d, bk, p.prescale, rng, b, rec);
             __syncwarp();
             if (wl == 0 && atom_add_acq_rel_cta(&s_done_a[dstp], 1u) + 1u == expect) st_release_sys(flag, p.epoch);
           }
+          base += nb;
         } else {
+          const int bits = block_bits(d);
           load_block<T>(data, d, p.prescale, tile.acc);
           __syncthreads();
           compute_meta(tile.acc, n, d.bucket, bits, tile.meta, tile.inv);
@@ -271,7 +355,7 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const Sr
       const uint32_t expect = s_expect[r];
       const uint8_t* src_rec[kMaxPeers];
       uint8_t* dst_rec[kMaxPeers];
-      uint32_t it = 0;
+      uint32_t base = 0;
       for (uint32_t b = b0; b < b1; ++b) {
         const BlockDesc d = p.blocks[b];
         int np = 0;
@@ -282,67 +366,35 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const Sr
           ++np;
         }
         const uint32_t n = block_n(d);
-        const int bits = block_bits(d);
         T* blk = data + d.elem_off;
         const bool aligned = (reinterpret_cast<uintptr_t>(blk) & 15u) == 0;
-        bool finished = false;  // did this warp/thread complete the chunk?
+        const uint32_t first = (warp - base) & (kNumWarps - 1);
+        bool finished = false;  // did this warp complete the chunk?
         if (block_is_raw(d)) {
           const uint32_t ni = div_up(n, kRawItemElems);
-          for (uint32_t i = 0; i < ni; ++i) {
-            if ((it++) % nwarps != warp) continue;
+          for (uint32_t i = first; i < ni; i += kNumWarps) {
             warp_reduce_raw<T>(blk, aligned, n, i, p.prescale, src_rec, np, dst_rec, np);
             __syncwarp();
             uint32_t last = 0;
             if (wl == 0) last = (atom_add_acq_rel_cta(&s_done_b, 1u) + 1u == expect) ? 1u : 0u;
             finished |= __shfl_sync(0xffffffffu, last, 0) != 0;
           }
+          base += ni;
         } else if (block_is_fast(d)) {
           const uint32_t nb = block_num_buckets(n, d.bucket);
-          const uint32_t meta_bytes = block_meta_bytes(n, d.bucket);
-          for (uint32_t bk = 0; bk < nb; ++bk) {
-            if ((it++) % nwarps != warp) continue;
-            const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
-            float x[kMaxGpl][8];
-            BucketCtx c;
-            // own slice + the W-1 decoded peer copies, summed in fixed rank order
-            auto gather = [&](uint32_t sl) {
-              c = make_slice_ctx(d, bk, sl);
-              warp_load_bucket<T>(blk, aligned, c, p.prescale, x);
-              // peers in batches of 4: all loads of a batch are issued before any is consumed
-              for (int q0 = 0; q0 < np; q0 += 4) {
-                uint64_t w[4][kMaxGpl];
-                BucketMeta pm[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (q0 + u < np) warp_fetch_peer(src_rec[q0 + u], meta_bytes, bk, bits, c, w[u], pm[u]);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (q0 + u < np) warp_accumulate(w[u], pm[u], bits, c, x);
-              }
-            };
-            float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-            for (uint32_t sl = 0; sl < ns; ++sl) {
-              gather(sl);
-              warp_minmax_update(x, c, mn, mx);
-            }
-            const BucketMeta m = warp_minmax_finish(mn, mx, bits);
-            warp_store_meta(m, bk, dst_rec, np);
-            if (ns == 1) {
-              warp_quantize_store<T, true>(x, c, m, bits, bk, meta_bytes, rng, b, dst_rec, np, blk, aligned);
-            } else {
-              // NB: the self-decode of slice sl overwrites only slice sl of my own gradient, which
-              // later slices never re-read
-              for (uint32_t sl = 0; sl < ns; ++sl) {
-                gather(sl);
-                warp_quantize_store<T, true>(x, c, m, bits, bk, meta_bytes, rng, b, dst_rec, np, blk, aligned);
-              }
-            }
+          for (uint32_t bk = first; bk < nb; bk += kNumWarps) {
+            if (bucket_is_full(d, bk, aligned))
+              bucket_reduce<T, true>(blk, aligned, d, bk, p.prescale, rng, b, src_rec, dst_rec, np);
+            else
+              bucket_reduce<T, false>(blk, aligned, d, bk, p.prescale, rng, b, src_rec, dst_rec, np);
             __syncwarp();
             uint32_t last = 0;
             if (wl == 0) last = (atom_add_acq_rel_cta(&s_done_b, 1u) + 1u == expect) ? 1u : 0u;
             finished |= __shfl_sync(0xffffffffu, last, 0) != 0;
           }
+          base += nb;
         } else {
+          const int bits = block_bits(d);
           load_block<T>(data, d, p.prescale, tile.acc);
           __syncthreads();
           for (int k = 0; k < np; ++k) decode_add<T>(src_rec[k], d, tile.acc);
@@ -365,7 +417,7 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const Sr
 
   // ------------------------------------------------------------------ phase C
   {
-    uint32_t it = 0;
+    uint32_t base = 0;
     for (int s = 1; s < W; ++s) {
       const int q = (r + s) % W;
       const uint32_t b0 = p.lane_first[q * G + lane], b1 = p.lane_first[q * G + lane + 1];
@@ -391,28 +443,26 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const Sr
         const BlockDesc d = p.blocks[b];
         const uint8_t* rec = slot + d.wire_off;
         const uint32_t n = block_n(d);
-        const int bits = block_bits(d);
         T* blk = data + d.elem_off;
         const bool aligned = (reinterpret_cast<uintptr_t>(blk) & 15u) == 0;
+        const uint32_t first = (warp - base) & (kNumWarps - 1);
         if (block_is_raw(d)) {
           const uint32_t ni = div_up(n, kRawItemElems);
-          for (uint32_t i = 0; i < ni; ++i) {
-            if ((it++) % nwarps != warp) continue;
+          for (uint32_t i = first; i < ni; i += kNumWarps) {
             if (!ensure()) return;
             warp_copy_raw<T>(rec, blk, aligned, n, i);
           }
+          base += ni;
         } else if (block_is_fast(d)) {
           const uint32_t nb = block_num_buckets(n, d.bucket);
-          const uint32_t meta_bytes = block_meta_bytes(n, d.bucket);
-          for (uint32_t bk = 0; bk < nb; ++bk) {
-            if ((it++) % nwarps != warp) continue;
+          for (uint32_t bk = first; bk < nb; bk += kNumWarps) {
             if (!ensure()) return;
-            const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
-            for (uint32_t sl = 0; sl < ns; ++sl) {
-              const BucketCtx c = make_slice_ctx(d, bk, sl);
-              warp_decode_store<T>(rec, meta_bytes, bk, bits, c, blk, aligned);
-            }
+            if (bucket_is_full(d, bk, aligned))
+              bucket_recv<T, true>(rec, blk, aligned, d, bk);
+            else
+              bucket_recv<T, false>(rec, blk, aligned, d, bk);
           }
+          base += nb;
         } else {
           if (!ensure()) return;
           decode_store<T>(rec, d, data);

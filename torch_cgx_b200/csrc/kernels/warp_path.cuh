@@ -61,15 +61,15 @@ __device__ __forceinline__ BucketCtx make_slice_ctx(const BlockDesc& d, uint32_t
 }
 
 // x[k][j] = float(src[e0 + (k*32+lane)*8 + j]) * prescale
-template <typename T>
+// FULL: the slice has all 512 elements and is 16 B aligned -> no per-element predicates.
+template <typename T, bool FULL>
 __device__ __forceinline__ void warp_load_bucket(const T* __restrict__ blk, bool aligned, const BucketCtx& c,
                                                  float prescale, float (&x)[kMaxGpl][8]) {
   const uint32_t lane = threadIdx.x & 31u;
 #pragma unroll
   for (int k = 0; k < kMaxGpl; ++k) {
-    if (c.nv[k] == 0) continue;
     const T* p = blk + c.e0 + ((uint32_t)k * 32u + lane) * 8u;
-    if (c.nv[k] == 8 && aligned) {
+    if (FULL || (c.nv[k] == 8 && aligned)) {
       if (sizeof(T) == 4) {
         const uint4 a = *reinterpret_cast<const uint4*>(p);
         const uint4 b = *(reinterpret_cast<const uint4*>(p) + 1);
@@ -87,7 +87,8 @@ __device__ __forceinline__ void warp_load_bucket(const T* __restrict__ blk, bool
   }
 }
 
-// Issue the loads of one peer's packed words + meta for this bucket (no use yet).
+// Issue the loads of one peer's packed words + meta for this slice (no use yet).
+template <bool FULL>
 __device__ __forceinline__ void warp_fetch_peer(const uint8_t* rec, uint32_t meta_bytes, uint32_t bk, int bits,
                                                 const BucketCtx& c, uint64_t (&w)[kMaxGpl], BucketMeta& m) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -95,27 +96,34 @@ __device__ __forceinline__ void warp_fetch_peer(const uint8_t* rec, uint32_t met
   const uint8_t* pay = rec + meta_bytes;
 #pragma unroll
   for (int k = 0; k < kMaxGpl; ++k)
-    w[k] = (c.nv[k] > 0) ? load_group_word(pay, c.grp0 + (uint32_t)k * 32u + lane, bits) : 0ull;
+    w[k] = (FULL || c.nv[k] > 0) ? load_group_word(pay, c.grp0 + (uint32_t)k * 32u + lane, bits) : 0ull;
 }
 
+// level j of a packed word; 32-bit arithmetic when the whole group fits in 32 bits
+__device__ __forceinline__ uint32_t unpack_level(uint64_t w, int j, int bits) {
+  if (bits <= 4) return ((uint32_t)w >> (j * bits)) & ((1u << bits) - 1u);
+  return unpack1(w, j, bits);
+}
+
+template <bool FULL>
 __device__ __forceinline__ void warp_accumulate(const uint64_t (&w)[kMaxGpl], const BucketMeta& m, int bits,
                                                 const BucketCtx& c, float (&x)[kMaxGpl][8]) {
 #pragma unroll
   for (int k = 0; k < kMaxGpl; ++k) {
-    if (c.nv[k] == 0) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (j < c.nv[k]) x[k][j] += decode_level(unpack1(w[k], j, bits), m.unit, m.min);
+      if (FULL || j < c.nv[k]) x[k][j] += decode_level(unpack_level(w[k], j, bits), m.unit, m.min);
   }
 }
 
+template <bool FULL>
 __device__ __forceinline__ void warp_minmax_update(const float (&x)[kMaxGpl][8], const BucketCtx& c, float& mn,
                                                    float& mx) {
 #pragma unroll
   for (int k = 0; k < kMaxGpl; ++k) {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (j < c.nv[k]) {
+      if (FULL || j < c.nv[k]) {
         mn = nan_min(mn, x[k][j]);
         mx = nan_max(mx, x[k][j]);
       }
@@ -151,77 +159,79 @@ __device__ __forceinline__ void warp_store_meta(const BucketMeta& m, uint32_t bk
   }
 }
 
+__device__ __forceinline__ uint64_t pack_levels(const uint32_t (&q)[8], int bits) {
+  if (bits <= 4) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w |= q[j] << (j * bits);
+    return w;
+  }
+  return pack8(q, bits);
+}
+
+template <typename T>
+__device__ __forceinline__ void store_group_values(T* __restrict__ o, const float (&dec)[8], bool vec, int nv) {
+  if (vec) {
+    if (sizeof(T) == 4) {
+      *reinterpret_cast<uint4*>(o) = pack16<T>(dec);
+      *(reinterpret_cast<uint4*>(o) + 1) = pack16<T>(dec + 4);
+    } else {
+      *reinterpret_cast<uint4*>(o) = pack16<T>(dec);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nv) o[j] = DT<T>::from_float(dec[j]);
+  }
+}
+
 // Quantize the slice held in x, write its packed words to `ndst` records
 // and (SELF) the decoded values to the owner's gradient buffer.
-template <typename T, bool SELF>
+template <typename T, bool SELF, bool FULL>
 __device__ __forceinline__ void warp_quantize_store(const float (&x)[kMaxGpl][8], const BucketCtx& c,
-                                                    const BucketMeta& m, int bits, uint32_t bk,
-                                                    uint32_t meta_bytes, const RngKey& rng, uint32_t block_id,
-                                                    uint8_t* const* dst_rec, int ndst, T* __restrict__ own_blk,
-                                                    bool aligned) {
+                                                    const BucketMeta& m, int bits, uint32_t meta_bytes,
+                                                    const RngKey& rng, uint32_t block_id, uint8_t* const* dst_rec,
+                                                    int ndst, T* __restrict__ own_blk, bool aligned) {
   const uint32_t lane = threadIdx.x & 31u;
   const float iv = inv_unit(m.unit);
   const float maxlvl = (float)max_level(bits);
-  (void)bk;
 #pragma unroll
   for (int k = 0; k < kMaxGpl; ++k) {
-    if (c.nv[k] == 0) continue;
+    if (!FULL && c.nv[k] == 0) continue;
     const uint32_t g = c.grp0 + (uint32_t)k * 32u + lane;
     float r[8];
     rounding_offsets8(rng, block_id, g, r);
     uint32_t q[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) q[j] = (j < c.nv[k]) ? encode_level(x[k][j], m.min, iv, r[j], maxlvl) : 0u;
-    const uint64_t w = pack8(q, bits);
+    for (int j = 0; j < 8; ++j) q[j] = (FULL || j < c.nv[k]) ? encode_level(x[k][j], m.min, iv, r[j], maxlvl) : 0u;
+    const uint64_t w = pack_levels(q, bits);
     for (int d = 0; d < ndst; ++d) store_group_word(dst_rec[d] + meta_bytes, g, bits, w);
     if (SELF) {
       float dec[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) dec[j] = decode_level(q[j], m.unit, m.min);
       T* o = own_blk + c.e0 + ((uint32_t)k * 32u + lane) * 8u;
-      if (c.nv[k] == 8 && aligned) {
-        if (sizeof(T) == 4) {
-          *reinterpret_cast<uint4*>(o) = pack16<T>(dec);
-          *(reinterpret_cast<uint4*>(o) + 1) = pack16<T>(dec + 4);
-        } else {
-          *reinterpret_cast<uint4*>(o) = pack16<T>(dec);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < c.nv[k]) o[j] = DT<T>::from_float(dec[j]);
-      }
+      store_group_values<T>(o, dec, FULL || (c.nv[k] == 8 && aligned), c.nv[k]);
     }
   }
 }
 
-// Decode one bucket of a (peer-written) record into the gradient buffer.
-template <typename T>
+// Decode one slice of a (peer-written) record into the gradient buffer.
+template <typename T, bool FULL>
 __device__ __forceinline__ void warp_decode_store(const uint8_t* rec, uint32_t meta_bytes, uint32_t bk, int bits,
                                                   const BucketCtx& c, T* __restrict__ own_blk, bool aligned) {
   const uint32_t lane = threadIdx.x & 31u;
   uint64_t w[kMaxGpl];
   BucketMeta m;
-  warp_fetch_peer(rec, meta_bytes, bk, bits, c, w, m);
+  warp_fetch_peer<FULL>(rec, meta_bytes, bk, bits, c, w, m);
 #pragma unroll
   for (int k = 0; k < kMaxGpl; ++k) {
-    if (c.nv[k] == 0) continue;
+    if (!FULL && c.nv[k] == 0) continue;
     float dec[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dec[j] = decode_level(unpack1(w[k], j, bits), m.unit, m.min);
+    for (int j = 0; j < 8; ++j) dec[j] = decode_level(unpack_level(w[k], j, bits), m.unit, m.min);
     T* o = own_blk + c.e0 + ((uint32_t)k * 32u + lane) * 8u;
-    if (c.nv[k] == 8 && aligned) {
-      if (sizeof(T) == 4) {
-        *reinterpret_cast<uint4*>(o) = pack16<T>(dec);
-        *(reinterpret_cast<uint4*>(o) + 1) = pack16<T>(dec + 4);
-      } else {
-        *reinterpret_cast<uint4*>(o) = pack16<T>(dec);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < c.nv[k]) o[j] = DT<T>::from_float(dec[j]);
-    }
+    store_group_values<T>(o, dec, FULL || (c.nv[k] == 8 && aligned), c.nv[k]);
   }
 }
 
