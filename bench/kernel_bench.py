@@ -41,6 +41,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/kernel_bench.json")
     ap.add_argument("--sizes-mb", default="1,8,25,64,256")
+    ap.add_argument("--lanes", type=int, default=148)
+    ap.add_argument("--bits", default="2,4,8")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     peaks = {}
@@ -52,7 +54,7 @@ def main():
     rows = []
     for mb in [int(x) for x in args.sizes_mb.split(",")]:
         for dtype in (torch.float32, torch.bfloat16):
-            for bits in (2, 4, 8):
+            for bits in [int(b) for b in args.bits.split(",")]:
                 n = (mb << 20) // (4 if dtype == torch.float32 else 2)
                 x = torch.randn(n, device=dev).to(dtype)
                 layers = [(0, n, bits, 512)]
@@ -61,7 +63,7 @@ def main():
                 wire = cgx.ops.wire_bytes(n, bits, 512, es)
                 tq = time_op(lambda: C.quantize(x, layers, 1, 1, False, 1.0, False, 0, 0, 0, 0, 2048), flush)
                 td = time_op(lambda: C.dequantize(w, x, layers, 1, 1, False, 2048), flush)
-                g = C.LocalSraGroup(1, 148, max(64 << 20, n * es + (1 << 20)), 5000, 2048)
+                g = C.LocalSraGroup(1, args.lanes, max(64 << 20, n * es + (1 << 20)), 5000, 2048)
                 y = x.clone()
                 tf = time_op(lambda: g.allreduce([y], layers), flush)
                 row = {

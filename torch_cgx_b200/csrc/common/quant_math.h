@@ -88,9 +88,10 @@ CGX_HD uint32_t encode_level(float x, float mn, float inv, float r, float maxlvl
 #else
   float t = std::fmaf(x - mn, inv, r);
 #endif
-  // fminf/fmaxf return the non-NaN operand: NaN -> maxlvl on host and device.
-  t = fmaxf(fminf(t, maxlvl_f), 0.f);
-  return (uint32_t)t;  // t >= 0 so truncation == floor
+  // t >= 0 always (x >= min, inv >= 0, r >= 0) unless it is NaN; fminf returns the
+  // non-NaN operand on host and device, so NaN -> maxlvl.
+  t = fminf(t, maxlvl_f);
+  return (uint32_t)t;  // truncation == floor for t >= 0
 }
 
 CGX_HD float decode_level(uint32_t q, float unit, float mn) {

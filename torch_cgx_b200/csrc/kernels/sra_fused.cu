@@ -155,15 +155,14 @@ __global__ void __launch_bounds__(kSraThreads, 2) sra_fused_kernel(const SraPara
 // shared-memory counters and published by whichever warp finishes last.
 // ===========================================================================
 constexpr uint32_t kNumWarps = kSraThreads / 32;
-constexpr int kPeerBatch = 2;  // peers whose packed words are in flight together (register budget)
 #define CGX_INF_POS __int_as_float(0x7f800000)
 #define CGX_INF_NEG __int_as_float(0xff800000)
 
 // phase A: my copy of one bucket of a peer's chunk -> quantize -> peer's slot
-template <typename T, bool FULL>
+template <typename T, bool FULL, int KB>
 __device__ __forceinline__ void bucket_send(const T* __restrict__ blk, bool aligned, const BlockDesc& d, uint32_t bk,
                                             float prescale, const RngKey& rng, uint32_t b, uint8_t* rec) {
-  const int bits = block_bits(d);
+  const int bits = KB ? KB : block_bits(d);
   const uint32_t meta_bytes = block_meta_bytes(block_n(d), d.bucket);
   const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
   float x[kMaxGpl][8];
@@ -188,7 +187,7 @@ __device__ __forceinline__ void bucket_send(const T* __restrict__ blk, bool alig
 }
 
 // own slice + the W-1 decoded peer copies, summed in fixed rank order
-template <typename T, bool FULL>
+template <typename T, bool FULL, int KB, int kPeerBatch>
 __device__ __forceinline__ void slice_gather(T* __restrict__ blk, bool aligned, const BlockDesc& d, uint32_t bk,
                                              uint32_t sl, float prescale, uint32_t meta_bytes, int bits,
                                              const uint8_t* const* src_rec, int np, BucketCtx& c,
@@ -209,18 +208,18 @@ __device__ __forceinline__ void slice_gather(T* __restrict__ blk, bool aligned, 
 }
 
 // phase B: reduce one bucket of MY chunk, requantize, publish to every peer, self-decode
-template <typename T, bool FULL>
+template <typename T, bool FULL, int KB, int kPeerBatch>
 __device__ __forceinline__ void bucket_reduce(T* __restrict__ blk, bool aligned, const BlockDesc& d, uint32_t bk,
                                               float prescale, const RngKey& rng, uint32_t b,
                                               const uint8_t* const* src_rec, uint8_t* const* dst_rec, int np) {
-  const int bits = block_bits(d);
+  const int bits = KB ? KB : block_bits(d);
   const uint32_t meta_bytes = block_meta_bytes(block_n(d), d.bucket);
   const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
   float x[kMaxGpl][8];
   float mn = CGX_INF_POS, mx = CGX_INF_NEG;
   BucketCtx c;
   for (uint32_t sl = 0; sl < ns; ++sl) {
-    slice_gather<T, FULL>(blk, aligned, d, bk, sl, prescale, meta_bytes, bits, src_rec, np, c, x);
+    slice_gather<T, FULL, KB, kPeerBatch>(blk, aligned, d, bk, sl, prescale, meta_bytes, bits, src_rec, np, c, x);
     warp_minmax_update<FULL>(x, c, mn, mx);
   }
   const BucketMeta m = warp_minmax_finish(mn, mx, bits);
@@ -231,17 +230,17 @@ __device__ __forceinline__ void bucket_reduce(T* __restrict__ blk, bool aligned,
     // the self-decode of slice sl overwrites only slice sl of my own gradient, which later
     // slices never re-read
     for (uint32_t sl = 0; sl < ns; ++sl) {
-      slice_gather<T, FULL>(blk, aligned, d, bk, sl, prescale, meta_bytes, bits, src_rec, np, c, x);
+      slice_gather<T, FULL, KB, kPeerBatch>(blk, aligned, d, bk, sl, prescale, meta_bytes, bits, src_rec, np, c, x);
       warp_quantize_store<T, true, FULL>(x, c, m, bits, meta_bytes, rng, b, dst_rec, np, blk, aligned);
     }
   }
 }
 
 // phase C: a peer's reduced bucket -> my gradient buffer
-template <typename T, bool FULL>
+template <typename T, bool FULL, int KB>
 __device__ __forceinline__ void bucket_recv(const uint8_t* rec, T* __restrict__ blk, bool aligned, const BlockDesc& d,
                                             uint32_t bk) {
-  const int bits = block_bits(d);
+  const int bits = KB ? KB : block_bits(d);
   const uint32_t meta_bytes = block_meta_bytes(block_n(d), d.bucket);
   const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
   for (uint32_t sl = 0; sl < ns; ++sl) {
@@ -254,8 +253,14 @@ __device__ __forceinline__ bool bucket_is_full(const BlockDesc& d, uint32_t bk, 
   return aligned && (bucket_count(d, bk) % kSliceElems) == 0;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const SraParams p) {
+// KB: compile-time quantization bits when every compressed block of the plan uses
+// the same width (the normal case) -- shifts/masks become immediates and the
+// per-width switches fold away; KB == 0 keeps them as run-time values.
+// kPeerBatch / kMinBlocks trade phase-B memory-level parallelism against occupancy:
+//   <2,1>: 128 registers, 16 warps/SM, two peers' words in flight per bucket
+//   <1,2>:  64 registers, 32 warps/SM (2 CTAs/SM), one peer at a time
+template <typename T, int KB, int kPeerBatch, int kMinBlocks>
+__global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel(const SraParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Tile& tile = *reinterpret_cast<Tile*>(smem_raw);
   __shared__ uint32_t s_expect[kMaxPeers];
@@ -313,9 +318,9 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const Sr
           const uint32_t nb = block_num_buckets(n, d.bucket);
           for (uint32_t bk = first; bk < nb; bk += kNumWarps) {
             if (bucket_is_full(d, bk, aligned))
-              bucket_send<T, true>(blk, aligned, d, bk, p.prescale, rng, b, rec);
+              bucket_send<T, true, KB>(blk, aligned, d, bk, p.prescale, rng, b, rec);
             else
-              bucket_send<T, false>(blk, aligned, d, bk, p.prescale, rng, b, rec);
+              bucket_send<T, false, KB>(blk, aligned, d, bk, p.prescale, rng, b, rec);
             __syncwarp();
             if (wl == 0 && atom_add_acq_rel_cta(&s_done_a[dstp], 1u) + 1u == expect) st_release_sys(flag, p.epoch);
           }
@@ -384,9 +389,9 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const Sr
           const uint32_t nb = block_num_buckets(n, d.bucket);
           for (uint32_t bk = first; bk < nb; bk += kNumWarps) {
             if (bucket_is_full(d, bk, aligned))
-              bucket_reduce<T, true>(blk, aligned, d, bk, p.prescale, rng, b, src_rec, dst_rec, np);
+              bucket_reduce<T, true, KB, kPeerBatch>(blk, aligned, d, bk, p.prescale, rng, b, src_rec, dst_rec, np);
             else
-              bucket_reduce<T, false>(blk, aligned, d, bk, p.prescale, rng, b, src_rec, dst_rec, np);
+              bucket_reduce<T, false, KB, kPeerBatch>(blk, aligned, d, bk, p.prescale, rng, b, src_rec, dst_rec, np);
             __syncwarp();
             uint32_t last = 0;
             if (wl == 0) last = (atom_add_acq_rel_cta(&s_done_b, 1u) + 1u == expect) ? 1u : 0u;
@@ -458,9 +463,9 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_fused_warp_kernel(const Sr
           for (uint32_t bk = first; bk < nb; bk += kNumWarps) {
             if (!ensure()) return;
             if (bucket_is_full(d, bk, aligned))
-              bucket_recv<T, true>(rec, blk, aligned, d, bk);
+              bucket_recv<T, true, KB>(rec, blk, aligned, d, bk);
             else
-              bucket_recv<T, false>(rec, blk, aligned, d, bk);
+              bucket_recv<T, false, KB>(rec, blk, aligned, d, bk);
           }
           base += nb;
         } else {
@@ -481,15 +486,34 @@ cudaError_t launch_t(const SraParams& p, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(sra_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(Tile));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sra_fused_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(Tile));
-    if (e != cudaSuccess) return e;
+#define CGX_SET_SMEM(KB_)                                                                                   \
+  e = cudaFuncSetAttribute(sra_fused_warp_kernel<T, KB_, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                           (int)sizeof(Tile));                                                                \
+  if (e != cudaSuccess) return e;                                                                             \
+  e = cudaFuncSetAttribute(sra_fused_warp_kernel<T, KB_, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                           (int)sizeof(Tile));                                                                \
+  if (e != cudaSuccess) return e;
+    CGX_SET_SMEM(0) CGX_SET_SMEM(2) CGX_SET_SMEM(4) CGX_SET_SMEM(8)
     configured[dev & 63] = true;
   }
-  if (p.variant == 1)
+  if (p.variant == 1) {
     sra_fused_kernel<T><<<p.lanes, kSraThreads, sizeof(Tile), stream>>>(p);
-  else
-    sra_fused_warp_kernel<T><<<p.lanes, kSraThreads, sizeof(Tile), stream>>>(p);
+  } else {
+#define CGX_LAUNCH_WARP(KB_, PB_, MB_) \
+  sra_fused_warp_kernel<T, KB_, PB_, MB_><<<p.lanes, kSraThreads, sizeof(Tile), stream>>>(p)
+#define CGX_LAUNCH_WARP_KB(PB_, MB_)                          \
+  switch (p.uniform_bits) {                                   \
+    case 2: CGX_LAUNCH_WARP(2, PB_, MB_); break;              \
+    case 4: CGX_LAUNCH_WARP(4, PB_, MB_); break;              \
+    case 8: CGX_LAUNCH_WARP(8, PB_, MB_); break;              \
+    default: CGX_LAUNCH_WARP(0, PB_, MB_); break;             \
+  }
+    if (p.variant == 2) {
+      CGX_LAUNCH_WARP_KB(1, 2)
+    } else {
+      CGX_LAUNCH_WARP_KB(2, 1)
+    }
+  }
   return cudaGetLastError();
 }
 
@@ -499,11 +523,11 @@ int max_resident_t() {
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaFuncSetAttribute(sra_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile));
-  cudaFuncSetAttribute(sra_fused_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile));
+  cudaFuncSetAttribute(sra_fused_warp_kernel<T, 0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile));
   int per_sm2 = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sra_fused_kernel<T>, kSraThreads, sizeof(Tile)) !=
           cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, sra_fused_warp_kernel<T>, kSraThreads,
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, sra_fused_warp_kernel<T, 0, 2, 1>, kSraThreads,
                                                     sizeof(Tile)) != cudaSuccess)
     return 0;
   return sms * (per_sm < per_sm2 ? per_sm : per_sm2);

@@ -11,7 +11,11 @@ namespace cgx {
 FusedSra::FusedSra(SymmetricHeap* heap, int max_lanes, int64_t timeout_ms, uint32_t min_lane_elems)
     : heap_(heap), max_lanes_(max_lanes), timeout_ns_((uint64_t)timeout_ms * 1000000ull),
       min_lane_elems_(min_lane_elems) {
-  variant_ = env_str("CGX_KERNEL", "warp") == "block" ? 1 : 0;
+  {
+    // CGX_KERNEL: "warp" (default: 16 warps/SM, 128 regs), "warp2" (32 warps/SM, 64 regs), "block" (v1)
+    const std::string k = env_str("CGX_KERNEL", "warp");
+    variant_ = k == "block" ? 1 : (k == "warp2" ? 2 : 0);
+  }
   if (max_lanes_ < 1) max_lanes_ = 1;
   if ((uint32_t)max_lanes_ > heap_->layout().flag_stride) max_lanes_ = (int)heap_->layout().flag_stride;
 }
@@ -36,6 +40,13 @@ const DevicePlan* FusedSra::prepare(const std::vector<LayerSpec>& layers, int dt
   if (it == cache_.end()) {
     auto dp = std::make_unique<DevicePlan>();
     dp->plan = build_plan(layers, opt);
+    int ub = -1;
+    for (const BlockDesc& bd : dp->plan.blocks) {
+      if (block_is_raw(bd)) continue;
+      const int bb = block_bits(bd);
+      ub = (ub == -1 || ub == bb) ? bb : 0;
+    }
+    dp->uniform_bits = ub > 0 ? ub : 0;
     if (dp->plan.max_chunk_wire <= heap_->layout().slot_bytes && !dp->plan.blocks.empty()) {
       const size_t bb = dp->plan.blocks.size() * sizeof(BlockDesc);
       const size_t lb = dp->plan.lane_first.size() * sizeof(uint32_t);
@@ -82,6 +93,7 @@ void FusedSra::run(const DevicePlan& dp, void* data, float prescale, const RngPa
   p.status = heap_->status_device();
   p.timeout_ns = timeout_ns_;
   p.variant = variant_;
+  p.uniform_bits = dp.uniform_bits;
   cuda_check(launch_sra_fused(p, stream), "launch_sra_fused");
   ++launches_;
 }

@@ -21,6 +21,7 @@ struct DevicePlan {
   Plan plan;
   BlockDesc* d_blocks = nullptr;
   uint32_t* d_lane_first = nullptr;
+  int uniform_bits = 0;  // bits shared by every compressed block, or 0
 };
 
 class FusedSra {
