@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Compressed-allreduce bandwidth sweep (BASELINE.json configs[4]): message sizes
 1 KB - 1 GB x bits {2,4,8,32} on N GPUs, cgx fused P2P kernel vs stock NCCL
-ncclAllReduce on the same box.  Device-timed per iteration with CUDA events on
-the launching stream, L2 flushed between iterations, MAX over ranks, median of
-iterations.
+ncclAllReduce on the same box.  Device-timed with CUDA events on the launching
+stream around a batch of back-to-back calls (nccl-tests style) over a rotating
+set of buffers larger than L2, MAX over ranks, median of 3 repetitions.
 
   torchrun --nproc-per-node N bench/allreduce_sweep.py --out gpurun_out/sweep_N.json
 
@@ -36,24 +36,27 @@ def median(xs):
     return xs[len(xs) // 2]
 
 
-def time_allreduce(fn, flush, iters, warmup, dev):
-    for _ in range(warmup):
-        fn()
+def time_allreduce(fn, bufs, iters, warmup, dev):
+    """nccl-tests style: `iters` calls enqueued back to back between two CUDA events on the
+    launching stream (no host sync inside), each call on a different buffer of a rotating set
+    that is larger than L2 (or 64 buffers for tiny messages), MAX over ranks."""
+    nb = len(bufs)
+    for i in range(warmup):
+        fn(bufs[i % nb])
     torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
-        if flush is not None:
-            flush.zero_()
+    reps = []
+    for _ in range(3):
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for i in range(iters):
+            fn(bufs[i % nb])
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e3)
-    t = torch.tensor(ts, device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks, per iteration
+        reps.append(e0.elapsed_time(e1) * 1e3 / iters)
+    t = torch.tensor(reps, device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks, per repetition
     return median(t.tolist())
 
 
@@ -64,10 +67,9 @@ def main():
     ap.add_argument("--max-mb", type=int, default=1024)
     ap.add_argument("--bits", default="2,4,8,32")
     ap.add_argument("--dtype", default="float32")
-    ap.add_argument("--iters", type=int, default=15)
+    ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--bucket-size", type=int, default=512)
-    ap.add_argument("--no-flush", action="store_true")
     args = ap.parse_args()
 
     rank, world, local = cgx.map_launcher_env()
@@ -77,7 +79,6 @@ def main():
     nccl = dist.new_group(backend="nccl")
     dtype = getattr(torch, args.dtype)
     es = torch.empty((), dtype=dtype).element_size()
-    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     os.environ["CGX_COMPRESSION_BUCKET_SIZE"] = str(args.bucket_size)
     be = cgx.get_backend()
 
@@ -89,9 +90,11 @@ def main():
     rows = []
     for nbytes in sizes:
         n = nbytes // es
-        x = torch.randn(n, device=dev).to(dtype)
-        iters = args.iters if nbytes <= (256 << 20) else max(5, args.iters // 3)
-        t_nccl = time_allreduce(lambda: dist.all_reduce(x, group=nccl), flush, iters, args.warmup, dev)
+        # rotating buffers: total > 2x L2 (126 MB) so no call finds its input in cache
+        nbuf = max(2, min(64, (288 << 20) // nbytes + 1))
+        bufs = [torch.randn(n, device=dev).to(dtype) for _ in range(nbuf)]
+        iters = args.iters if nbytes <= (64 << 20) else max(6, args.iters // 3)
+        t_nccl = time_allreduce(lambda x: dist.all_reduce(x, group=nccl), bufs, iters, args.warmup, dev)
         row_base = {"bytes": nbytes, "dtype": args.dtype, "world": world}
         r = dict(row_base, impl="nccl", bits=32, time_us=round(t_nccl, 2),
                  algbw_gbs=round(nbytes / t_nccl / 1e3, 2), busbw_gbs=round(nbytes / t_nccl / 1e3 * 2 * (world - 1) / world, 2))
@@ -100,9 +103,10 @@ def main():
             print(json.dumps(r), flush=True)
         for bits in [int(b) for b in args.bits.split(",")]:
             os.environ["CGX_COMPRESSION_QUANTIZATION_BITS"] = str(bits)
-            x.normal_()
+            for x in bufs:
+                x.normal_()
             be.reset_stats()
-            t = time_allreduce(lambda: dist.all_reduce(x), flush, iters, args.warmup, dev)
+            t = time_allreduce(lambda x: dist.all_reduce(x), bufs, iters, args.warmup, dev)
             st = be.stats()
             wire_per_call = st[3] / max(1, st[0])
             r = dict(row_base, impl="cgx", bits=bits, time_us=round(t, 2), algbw_gbs=round(nbytes / t / 1e3, 2),
@@ -113,11 +117,11 @@ def main():
             rows.append(r)
             if rank == 0:
                 print(json.dumps(r), flush=True)
-        del x
+        del bufs
     if rank == 0:
         Path(args.out).parent.mkdir(parents=True, exist_ok=True)
         Path(args.out).write_text(json.dumps({"world": world, "lanes": be.lanes(), "rows": rows,
-                                              "timing": "CUDA events per iteration, L2 flushed, max over ranks, median"}, indent=1))
+                                              "timing": "CUDA events around `iters` back-to-back calls on rotating buffers (> 2x L2 in total), max over ranks, median of 3 repetitions"}, indent=1))
     dist.barrier()
     dist.destroy_process_group()
 
