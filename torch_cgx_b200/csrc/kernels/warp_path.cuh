@@ -20,7 +20,7 @@ namespace dev {
 
 constexpr int kMaxGpl = 2;             // pack groups (of 8 values) per lane and slice
 constexpr uint32_t kSliceElems = 256u * kMaxGpl;
-constexpr uint32_t kRawItemElems = 2048;  // raw (uncompressed) blocks are cut into warp items of this size
+constexpr uint32_t kRawItemElems = 512;  // raw (uncompressed) blocks are cut into warp items of this size
 
 __device__ __forceinline__ bool block_is_fast(const BlockDesc& d) {
   return block_bits(d) <= 8 && (d.bucket & 255u) == 0;
@@ -236,24 +236,59 @@ __device__ __forceinline__ void warp_decode_store(const uint8_t* rec, uint32_t m
 }
 
 // ---- raw (uncompressed) warp items -----------------------------------------
-// item `it` of a raw block covers elements [it*kRawItemElems, ...) of the block.
+// item `it` of a raw block covers elements [it*kRawItemElems, ...) of the block:
+// kRawU 16-byte vectors per lane, all loads of a source issued before any use.
+template <typename T>
+struct RawCfg {
+  static constexpr int V = DT<T>::kVec;
+  static constexpr int U = (int)(kRawItemElems / (32u * V));  // vectors per lane and item
+};
+
+template <typename T>
+__device__ __forceinline__ void raw_load_own(const T* __restrict__ blk, bool aligned, uint32_t n, uint32_t lo,
+                                             float prescale, float (&f)[RawCfg<T>::U][RawCfg<T>::V]) {
+  constexpr int V = RawCfg<T>::V, U = RawCfg<T>::U;
+  const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint32_t i0 = lo + ((uint32_t)u * 32u + lane) * V;
+    if (aligned && i0 + V <= n) {
+      unpack16<T>(*reinterpret_cast<const uint4*>(blk + i0), f[u]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) f[u][k] = (i0 + k < n) ? DT<T>::to_float(blk[i0 + k]) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) f[u][k] *= prescale;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void raw_store_own(T* __restrict__ blk, bool aligned, uint32_t n, uint32_t i0,
+                                              const uint4& packed) {
+  constexpr int V = RawCfg<T>::V;
+  if (aligned && i0 + V <= n) {
+    *reinterpret_cast<uint4*>(blk + i0) = packed;
+  } else {
+    const T* pe = reinterpret_cast<const T*>(&packed);
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+      if (i0 + k < n) blk[i0 + k] = pe[k];
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void warp_send_raw(const T* __restrict__ blk, bool aligned, uint32_t n, uint32_t it,
                                               float prescale, uint8_t* rec) {
-  constexpr int V = DT<T>::kVec;
+  constexpr int V = RawCfg<T>::V, U = RawCfg<T>::U;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t lo = it * kRawItemElems, hi = min(n, lo + kRawItemElems);
-  for (uint32_t i0 = lo + lane * V; i0 < hi; i0 += 32u * V) {
-    float f[V];
-    if (aligned && i0 + V <= n) {
-      unpack16<T>(*reinterpret_cast<const uint4*>(blk + i0), f);
-    } else {
+  const uint32_t lo = it * kRawItemElems;
+  float f[U][V];
+  raw_load_own<T>(blk, aligned, n, lo, prescale, f);
 #pragma unroll
-      for (int k = 0; k < V; ++k) f[k] = (i0 + k < n) ? DT<T>::to_float(blk[i0 + k]) : 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < V; ++k) f[k] *= prescale;
-    st_v4(rec + (size_t)i0 * sizeof(T), pack16<T>(f));
+  for (int u = 0; u < U; ++u) {
+    const uint32_t i0 = lo + ((uint32_t)u * 32u + lane) * V;
+    if (i0 < n) st_v4(rec + (size_t)i0 * sizeof(T), pack16<T>(f[u]));
   }
 }
 
@@ -261,37 +296,32 @@ template <typename T>
 __device__ __forceinline__ void warp_reduce_raw(T* __restrict__ blk, bool aligned, uint32_t n, uint32_t it,
                                                 float prescale, const uint8_t* const* peer_rec, int npeer,
                                                 uint8_t* const* dst_rec, int ndst) {
-  constexpr int V = DT<T>::kVec;
+  constexpr int V = RawCfg<T>::V, U = RawCfg<T>::U;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t lo = it * kRawItemElems, hi = min(n, lo + kRawItemElems);
-  for (uint32_t i0 = lo + lane * V; i0 < hi; i0 += 32u * V) {
-    const bool full = aligned && i0 + V <= n;
-    float f[V];
-    if (full) {
-      unpack16<T>(*reinterpret_cast<const uint4*>(blk + i0), f);
-    } else {
+  const uint32_t lo = it * kRawItemElems;
+  float f[U][V];
+  raw_load_own<T>(blk, aligned, n, lo, prescale, f);
+  for (int q = 0; q < npeer; ++q) {
+    uint4 pw[U];
 #pragma unroll
-      for (int k = 0; k < V; ++k) f[k] = (i0 + k < n) ? DT<T>::to_float(blk[i0 + k]) : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i0 = lo + ((uint32_t)u * 32u + lane) * V;
+      pw[u] = (i0 < n) ? ld_sys_v4(peer_rec[q] + (size_t)i0 * sizeof(T)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int k = 0; k < V; ++k) f[k] *= prescale;
-    uint4 pw[kMaxPeers];
-    for (int q = 0; q < npeer; ++q) pw[q] = ld_sys_v4(peer_rec[q] + (size_t)i0 * sizeof(T));
-    for (int q = 0; q < npeer; ++q) {
+    for (int u = 0; u < U; ++u) {
       float g[V];
-      unpack16<T>(pw[q], g);
+      unpack16<T>(pw[u], g);
 #pragma unroll
-      for (int k = 0; k < V; ++k) f[k] += g[k];
+      for (int k = 0; k < V; ++k) f[u][k] += g[k];
     }
-    const uint4 packed = pack16<T>(f);
-    if (full) {
-      *reinterpret_cast<uint4*>(blk + i0) = packed;
-    } else {
-      const T* pe = reinterpret_cast<const T*>(&packed);
+  }
 #pragma unroll
-      for (int k = 0; k < V; ++k)
-        if (i0 + k < n) blk[i0 + k] = pe[k];
-    }
+  for (int u = 0; u < U; ++u) {
+    const uint32_t i0 = lo + ((uint32_t)u * 32u + lane) * V;
+    if (i0 >= n) continue;
+    const uint4 packed = pack16<T>(f[u]);
+    raw_store_own<T>(blk, aligned, n, i0, packed);
     for (int d = 0; d < ndst; ++d) st_v4(dst_rec[d] + (size_t)i0 * sizeof(T), packed);
   }
 }
@@ -299,19 +329,19 @@ __device__ __forceinline__ void warp_reduce_raw(T* __restrict__ blk, bool aligne
 template <typename T>
 __device__ __forceinline__ void warp_copy_raw(const uint8_t* rec, T* __restrict__ blk, bool aligned, uint32_t n,
                                               uint32_t it) {
-  constexpr int V = DT<T>::kVec;
+  constexpr int V = RawCfg<T>::V, U = RawCfg<T>::U;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t lo = it * kRawItemElems, hi = min(n, lo + kRawItemElems);
-  for (uint32_t i0 = lo + lane * V; i0 < hi; i0 += 32u * V) {
-    const uint4 raw = ld_sys_v4(rec + (size_t)i0 * sizeof(T));
-    if (aligned && i0 + V <= n) {
-      *reinterpret_cast<uint4*>(blk + i0) = raw;
-    } else {
-      const T* pe = reinterpret_cast<const T*>(&raw);
+  const uint32_t lo = it * kRawItemElems;
+  uint4 pw[U];
 #pragma unroll
-      for (int k = 0; k < V; ++k)
-        if (i0 + k < n) blk[i0 + k] = pe[k];
-    }
+  for (int u = 0; u < U; ++u) {
+    const uint32_t i0 = lo + ((uint32_t)u * 32u + lane) * V;
+    pw[u] = (i0 < n) ? ld_sys_v4(rec + (size_t)i0 * sizeof(T)) : make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint32_t i0 = lo + ((uint32_t)u * 32u + lane) * V;
+    if (i0 < n) raw_store_own<T>(blk, aligned, n, i0, pw[u]);
   }
 }
 
