@@ -148,5 +148,13 @@ def _ddp_gpu(rank, world):
 
 
 @pytest.mark.multigpu
+def test_reference_suite_all_gpus():
+    n = torch.cuda.device_count()
+    if n < 4:
+        pytest.skip("needs >= 4 GPUs")
+    spawn(_reference_suite, min(n, 8), timeout=900)
+
+
+@pytest.mark.multigpu
 def test_ddp_hook_two_gpus():
     spawn(_ddp_gpu, 2, timeout=600)
