@@ -263,7 +263,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("lanes", &ProcessGroupCGX::lanes)
       .def("stats", &ProcessGroupCGX::stats)
       .def("reset_stats", &ProcessGroupCGX::reset_stats)
-      .def("check_health", &ProcessGroupCGX::check_health);
+      .def("check_health", &ProcessGroupCGX::check_health)
+      .def("enable_trace", &ProcessGroupCGX::enable_trace)
+      .def("read_trace", &ProcessGroupCGX::read_trace);
 
   m.def("create_backend", &create_backend, py::arg("store"), py::arg("rank"), py::arg("size"), py::arg("timeout"),
         py::arg("cpu_delegate"), py::arg("cuda_delegate"), py::call_guard<py::gil_scoped_release>());

@@ -30,6 +30,7 @@ struct SraParams {
   uint32_t* status;              // local error word (0 = ok)
   uint64_t timeout_ns;
   int variant;                   // 0 = warp-centric kernel (default), 1 = CTA/shared-memory kernel (v1)
+  unsigned long long* trace;     // optional [lanes][8] device timestamps (ns, globaltimer), nullptr = off
   int uniform_bits;              // common bits of all compressed blocks (2/4/8 select a specialised kernel), else 0
 };
 

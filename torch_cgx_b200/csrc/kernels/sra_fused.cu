@@ -155,6 +155,17 @@ __global__ void __launch_bounds__(kSraThreads, 2) sra_fused_kernel(const SraPara
 // shared-memory counters and published by whichever warp finishes last.
 // ===========================================================================
 constexpr uint32_t kNumWarps = kSraThreads / 32;
+
+// Tracing: per-lane phase timestamps (slot 0: kernel start [min], 1: phase A done,
+// 2: phase B inputs arrived, 3: phase B done, 4: last phase-C wait satisfied, 5: end [max]).
+__device__ __forceinline__ void trace_mark(unsigned long long* trace, int lane, int slot, bool is_min = false) {
+  if (trace == nullptr || (threadIdx.x & 31u) != 0) return;
+  const unsigned long long t = globaltimer_ns();
+  if (is_min)
+    atomicMin(&trace[(size_t)lane * 8 + slot], t);
+  else
+    atomicMax(&trace[(size_t)lane * 8 + slot], t);
+}
 #define CGX_INF_POS __int_as_float(0x7f800000)
 #define CGX_INF_NEG __int_as_float(0xff800000)
 
@@ -286,6 +297,7 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
     s_abort = 0;
   }
   __syncthreads();
+  trace_mark(p.trace, lane, 0, true);
 
   // ------------------------------------------------------------------ phase A
   {
@@ -341,6 +353,7 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
     }
   }
 
+  trace_mark(p.trace, lane, 1);
   // ------------------------------------------------------------------ phase B
   {
     const uint32_t b0 = p.lane_first[r * G + lane], b1 = p.lane_first[r * G + lane + 1];
@@ -354,6 +367,7 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
         }
       }
       if (!__all_sync(0xffffffffu, ok)) return;
+      trace_mark(p.trace, lane, 2);
 
       RngKey rng = p.rng;
       rng.stream = (uint32_t)r * 2u + 1u;
@@ -420,6 +434,7 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
     }
   }
 
+  trace_mark(p.trace, lane, 3);
   // ------------------------------------------------------------------ phase C
   {
     uint32_t base = 0;
@@ -442,6 +457,7 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
         }
         ok = __shfl_sync(0xffffffffu, ok, 0);
         waited = true;
+        trace_mark(p.trace, lane, 4);
         return ok != 0;
       };
       for (uint32_t b = b0; b < b1; ++b) {
@@ -475,6 +491,7 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
       }
     }
   }
+  trace_mark(p.trace, lane, 5);
 }
 
 template <typename T>

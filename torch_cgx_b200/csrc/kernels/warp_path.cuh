@@ -82,8 +82,10 @@ __device__ __forceinline__ void warp_load_bucket(const T* __restrict__ blk, bool
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[k][j] = (j < c.nv[k]) ? DT<T>::to_float(p[j]) : 0.f;
     }
+    if (prescale != 1.0f) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[k][j] *= prescale;
+      for (int j = 0; j < 8; ++j) x[k][j] *= prescale;
+    }
   }
 }
 
@@ -100,8 +102,20 @@ __device__ __forceinline__ void warp_fetch_peer(const uint8_t* rec, uint32_t met
 }
 
 // level j of a packed word; 32-bit arithmetic when the whole group fits in 32 bits
+__device__ __forceinline__ uint32_t bfe32(uint32_t v, int pos, int len) {
+  uint32_t r;
+  asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(pos), "r"(len));
+  return r;
+}
+__device__ __forceinline__ uint32_t bfi32(uint32_t field, uint32_t base, int pos, int len) {
+  uint32_t r;
+  asm("bfi.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(field), "r"(base), "r"(pos), "r"(len));
+  return r;
+}
+// level j of a packed word: one bit-field extract on the 32-bit half that holds it
 __device__ __forceinline__ uint32_t unpack_level(uint64_t w, int j, int bits) {
-  if (bits <= 4) return ((uint32_t)w >> (j * bits)) & ((1u << bits) - 1u);
+  if (bits <= 4) return bfe32((uint32_t)w, j * bits, bits);
+  if (bits == 8) return bfe32(j < 4 ? (uint32_t)w : (uint32_t)(w >> 32), (j & 3) * 8, 8);
   return unpack1(w, j, bits);
 }
 
@@ -161,10 +175,19 @@ __device__ __forceinline__ void warp_store_meta(const BucketMeta& m, uint32_t bk
 
 __device__ __forceinline__ uint64_t pack_levels(const uint32_t (&q)[8], int bits) {
   if (bits <= 4) {
-    uint32_t w = 0;
+    uint32_t w = q[0];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) w |= q[j] << (j * bits);
+    for (int j = 1; j < 8; ++j) w = bfi32(q[j], w, j * bits, bits);
     return w;
+  }
+  if (bits == 8) {
+    uint32_t lo = q[0], hi = q[4];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+      lo = bfi32(q[j], lo, j * 8, 8);
+      hi = bfi32(q[4 + j], hi, j * 8, 8);
+    }
+    return (uint64_t)lo | ((uint64_t)hi << 32);
   }
   return pack8(q, bits);
 }
@@ -199,11 +222,16 @@ __device__ __forceinline__ void warp_quantize_store(const float (&x)[kMaxGpl][8]
   for (int k = 0; k < kMaxGpl; ++k) {
     if (!FULL && c.nv[k] == 0) continue;
     const uint32_t g = c.grp0 + (uint32_t)k * 32u + lane;
-    float r[8];
-    rounding_offsets8(rng, block_id, g, r);
     uint32_t q[8];
+    if (rng.enabled) {
+      float r[8];
+      rounding_offsets8(rng, block_id, g, r);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) q[j] = (FULL || j < c.nv[k]) ? encode_level(x[k][j], m.min, iv, r[j], maxlvl) : 0u;
+      for (int j = 0; j < 8; ++j) q[j] = (FULL || j < c.nv[k]) ? encode_level(x[k][j], m.min, iv, r[j], maxlvl) : 0u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[j] = (FULL || j < c.nv[k]) ? encode_level(x[k][j], m.min, iv, 0.5f, maxlvl) : 0u;
+    }
     const uint64_t w = pack_levels(q, bits);
     for (int d = 0; d < ndst; ++d) store_group_word(dst_rec[d] + meta_bytes, g, bits, w);
     if (SELF) {

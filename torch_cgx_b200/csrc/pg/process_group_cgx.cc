@@ -342,6 +342,21 @@ void ProcessGroupCGX::reset_stats() {
   if (engine_) engine_->reset_stats();
 }
 
+void ProcessGroupCGX::enable_trace(bool on) {
+  TORCH_CHECK(engine_ && engine_->has_p2p(), "cgx: enable_trace needs the P2P engine (call init_cuda first)");
+  c10::cuda::CUDAGuard g(device_);
+  engine_->fused()->enable_trace(on);
+}
+
+at::Tensor ProcessGroupCGX::read_trace() {
+  TORCH_CHECK(engine_ && engine_->has_p2p(), "cgx: read_trace needs the P2P engine");
+  c10::cuda::CUDAGuard g(device_);
+  std::vector<uint64_t> v = engine_->fused()->read_trace();
+  at::Tensor t = at::empty({(int64_t)v.size() / 8, 8}, at::kLong);
+  std::memcpy(t.data_ptr(), v.data(), v.size() * sizeof(uint64_t));
+  return t;
+}
+
 void ProcessGroupCGX::check_health() {
   if (engine_) engine_->check_health();
 }

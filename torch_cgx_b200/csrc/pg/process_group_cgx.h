@@ -125,6 +125,9 @@ class ProcessGroupCGX : public c10d::Backend {
   std::vector<int64_t> stats() const;  // calls, kernel launches, elements, wire bytes, raw bytes
   void reset_stats();
   void check_health();
+  // per-lane device timestamps of the last fused allreduce (see FusedSra::read_trace)
+  void enable_trace(bool on);
+  at::Tensor read_trace();
 
  private:
   c10::intrusive_ptr<c10d::Backend> delegate_for(const at::Tensor& t, const char* op);

@@ -20,7 +20,24 @@ FusedSra::FusedSra(SymmetricHeap* heap, int max_lanes, int64_t timeout_ms, uint3
   if ((uint32_t)max_lanes_ > heap_->layout().flag_stride) max_lanes_ = (int)heap_->layout().flag_stride;
 }
 
+void FusedSra::enable_trace(bool on) {
+  trace_on_ = on;
+  if (on && d_trace_ == nullptr)
+    cuda_check(cudaMalloc((void**)&d_trace_, (size_t)heap_->layout().flag_stride * 8 * sizeof(unsigned long long)),
+               "cudaMalloc(trace)");
+}
+
+std::vector<uint64_t> FusedSra::read_trace() {
+  std::vector<uint64_t> out;
+  if (d_trace_ == nullptr || last_lanes_ == 0) return out;
+  cuda_check(cudaDeviceSynchronize(), "trace sync");
+  out.resize((size_t)last_lanes_ * 8);
+  cuda_check(cudaMemcpy(out.data(), d_trace_, out.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost), "trace copy");
+  return out;
+}
+
 FusedSra::~FusedSra() {
+  if (d_trace_) cudaFree(d_trace_);
   for (auto& kv : cache_) {
     if (kv.second->d_blocks) cudaFree(kv.second->d_blocks);
     if (kv.second->d_lane_first) cudaFree(kv.second->d_lane_first);
@@ -92,6 +109,17 @@ void FusedSra::run(const DevicePlan& dp, void* data, float prescale, const RngPa
   }
   p.status = heap_->status_device();
   p.timeout_ns = timeout_ns_;
+  p.trace = nullptr;
+  if (trace_on_ && d_trace_) {
+    // slot 0 takes a minimum, the rest maxima: 0xFF.. / 0 initialisation per lane
+    std::vector<unsigned long long> init((size_t)dp.plan.lanes * 8, 0ull);
+    for (int l = 0; l < dp.plan.lanes; ++l) init[(size_t)l * 8] = ~0ull;
+    cuda_check(cudaMemcpyAsync(d_trace_, init.data(), init.size() * sizeof(unsigned long long),
+                               cudaMemcpyHostToDevice, stream),
+               "trace init");
+    p.trace = d_trace_;
+  }
+  last_lanes_ = dp.plan.lanes;
   p.variant = variant_;
   p.uniform_bits = dp.uniform_bits;
   cuda_check(launch_sra_fused(p, stream), "launch_sra_fused");

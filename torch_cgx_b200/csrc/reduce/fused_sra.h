@@ -45,6 +45,13 @@ class FusedSra {
 
   // throws std::runtime_error if a kernel reported a timeout
   void check_status();
+
+  // Tracing: when enabled, the next run() records per-lane phase timestamps
+  // (device globaltimer, ns); read_trace() synchronises the device and returns
+  // lanes x 8 values: [start, A done, B inputs ready, B done, last C wait, end, -, -].
+  void enable_trace(bool on);
+  std::vector<uint64_t> read_trace();
+  int last_lanes() const { return last_lanes_; }
   uint64_t launches() const { return launches_; }
   uint32_t epoch() const { return epoch_; }
 
@@ -56,6 +63,9 @@ class FusedSra {
   uint32_t epoch_ = 0;
   uint64_t launches_ = 0;
   int variant_ = 0;
+  unsigned long long* d_trace_ = nullptr;
+  bool trace_on_ = false;
+  int last_lanes_ = 0;
   std::unordered_map<uint64_t, std::unique_ptr<DevicePlan>> cache_;
 };
 
