@@ -71,9 +71,11 @@ __global__ void __launch_bounds__(kSraThreads, 2) sra_fused_kernel(const SraPara
         store_record(tile.meta, tile.pay, block_meta_bytes(n, d.bucket), block_payload_bytes(n, bits), &rec, 1);
         __syncthreads();
       }
-      __syncthreads();
-      if (tid == 0) st_release_sys(p.flags1[dstp] + (size_t)r * p.flag_stride + lane, p.epoch);
     }
+    // one release per lane for the whole phase (see the warp kernel)
+    __syncthreads();
+    if (tid < (uint32_t)W && (int)tid != r && p.lane_first[tid * G + lane] != p.lane_first[tid * G + lane + 1])
+      st_release_sys(p.flags1[tid] + (size_t)r * p.flag_stride + lane, p.epoch);
   }
 
   // ------------------------------------------------------------------ phase B
@@ -275,7 +277,8 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Tile& tile = *reinterpret_cast<Tile*>(smem_raw);
   __shared__ uint32_t s_expect[kMaxPeers];
-  __shared__ uint32_t s_done_a[kMaxPeers];
+  __shared__ uint32_t s_done_a;   // items of phase A finished by this CTA (all destinations)
+  __shared__ uint32_t s_total_a;  // items of phase A in this lane
   __shared__ uint32_t s_done_b;
   __shared__ int s_abort;
 
@@ -290,11 +293,18 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
     for (uint32_t b = p.lane_first[tid * G + lane]; b < p.lane_first[tid * G + lane + 1]; ++b)
       tot += block_items(p.blocks[b]);
     s_expect[tid] = tot;
-    s_done_a[tid] = 0;
   }
   if (tid == 0) {
+    s_done_a = 0;
     s_done_b = 0;
     s_abort = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t tot = 0;
+    for (int q = 0; q < W; ++q)
+      if (q != r) tot += s_expect[q];
+    s_total_a = tot;
   }
   __syncthreads();
   trace_mark(p.trace, lane, 0, true);
@@ -304,13 +314,23 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
     RngKey rng = p.rng;
     rng.stream = (uint32_t)r * 2u;
     uint32_t base = 0;  // items dealt so far: item i goes to warp (i % kNumWarps)
+    const uint32_t total_a = s_total_a;
+    // ONE system-scope release per lane for the whole phase: a fence.sys drains every
+    // outstanding NVLink store of the SM (microseconds), and the consumer needs all W-1
+    // sources before it can start phase B anyway, so per-destination signalling buys nothing.
+    auto item_done_a = [&]() {
+      __syncwarp();
+      uint32_t last = 0;
+      if (wl == 0) last = (atom_add_acq_rel_cta(&s_done_a, 1u) + 1u == total_a) ? 1u : 0u;
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last && wl < (uint32_t)W && (int)wl != r && s_expect[wl] > 0)
+        st_release_sys(p.flags1[wl] + (size_t)r * p.flag_stride + lane, p.epoch);
+    };
     for (int s = 1; s < W; ++s) {
       const int dstp = (r + s) % W;
       const uint32_t b0 = p.lane_first[dstp * G + lane], b1 = p.lane_first[dstp * G + lane + 1];
       if (b0 == b1) continue;
       uint8_t* slot = p.recv1[dstp] + (size_t)r * p.slot_bytes;
-      uint32_t* flag = p.flags1[dstp] + (size_t)r * p.flag_stride + lane;
-      const uint32_t expect = s_expect[dstp];
       for (uint32_t b = b0; b < b1; ++b) {
         const BlockDesc d = p.blocks[b];
         uint8_t* rec = slot + d.wire_off;
@@ -322,8 +342,7 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
           const uint32_t ni = div_up(n, kRawItemElems);
           for (uint32_t i = first; i < ni; i += kNumWarps) {
             warp_send_raw<T>(blk, aligned, n, i, p.prescale, rec);
-            __syncwarp();
-            if (wl == 0 && atom_add_acq_rel_cta(&s_done_a[dstp], 1u) + 1u == expect) st_release_sys(flag, p.epoch);
+            item_done_a();
           }
           base += ni;
         } else if (block_is_fast(d)) {
@@ -333,8 +352,7 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
               bucket_send<T, true, KB>(blk, aligned, d, bk, p.prescale, rng, b, rec);
             else
               bucket_send<T, false, KB>(blk, aligned, d, bk, p.prescale, rng, b, rec);
-            __syncwarp();
-            if (wl == 0 && atom_add_acq_rel_cta(&s_done_a[dstp], 1u) + 1u == expect) st_release_sys(flag, p.epoch);
+            item_done_a();
           }
           base += nb;
         } else {
@@ -347,7 +365,7 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
           __syncthreads();
           store_record(tile.meta, tile.pay, block_meta_bytes(n, d.bucket), block_payload_bytes(n, bits), &rec, 1);
           __syncthreads();
-          if (tid == 0 && atom_add_acq_rel_cta(&s_done_a[dstp], 1u) + 1u == expect) st_release_sys(flag, p.epoch);
+          if (warp == 0) item_done_a();
         }
       }
     }
