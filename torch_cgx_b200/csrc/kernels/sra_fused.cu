@@ -26,6 +26,8 @@
 #include "launch.h"
 #include "warp_path.cuh"
 
+#include <type_traits>
+
 namespace cgx {
 using namespace dev;
 
@@ -207,16 +209,20 @@ __device__ __forceinline__ void slice_gather(T* __restrict__ blk, bool aligned, 
                                              float (&x)[kMaxGpl][8]) {
   c = make_slice_ctx(d, bk, sl);
   warp_load_bucket<T, FULL>(blk, aligned, c, prescale, x);
-  // peers in batches: all loads of a batch are issued before any is consumed
-  for (int q0 = 0; q0 < np; q0 += kPeerBatch) {
-    uint64_t w[kPeerBatch][kMaxGpl];
-    BucketMeta pm[kPeerBatch];
+  // peers in batches: all loads of a batch are issued before any is consumed. With <= 4 bits a
+  // group's word is 32 bits, so twice as many peers fit in the same register budget.
+  constexpr bool kNarrow = (KB > 0 && KB <= 4);
+  using word_t = typename std::conditional<kNarrow, uint32_t, uint64_t>::type;
+  constexpr int kBatch = kNarrow ? kPeerBatch : kPeerBatch;
+  for (int q0 = 0; q0 < np; q0 += kBatch) {
+    word_t w[kBatch][kMaxGpl];
+    BucketMeta pm[kBatch];
 #pragma unroll
-    for (int u = 0; u < kPeerBatch; ++u)
-      if (q0 + u < np) warp_fetch_peer<FULL>(src_rec[q0 + u], meta_bytes, bk, bits, c, w[u], pm[u]);
+    for (int u = 0; u < kBatch; ++u)
+      if (q0 + u < np) warp_fetch_peer<FULL, word_t>(src_rec[q0 + u], meta_bytes, bk, bits, c, w[u], pm[u]);
 #pragma unroll
-    for (int u = 0; u < kPeerBatch; ++u)
-      if (q0 + u < np) warp_accumulate<FULL>(w[u], pm[u], bits, c, x);
+    for (int u = 0; u < kBatch; ++u)
+      if (q0 + u < np) warp_accumulate<FULL, word_t>(w[u], pm[u], bits, c, x);
   }
 }
 

@@ -90,15 +90,16 @@ __device__ __forceinline__ void warp_load_bucket(const T* __restrict__ blk, bool
 }
 
 // Issue the loads of one peer's packed words + meta for this slice (no use yet).
-template <bool FULL>
+// WORD = uint32_t when a group of 8 levels fits in 32 bits (bits <= 4), else uint64_t
+template <bool FULL, typename WORD>
 __device__ __forceinline__ void warp_fetch_peer(const uint8_t* rec, uint32_t meta_bytes, uint32_t bk, int bits,
-                                                const BucketCtx& c, uint64_t (&w)[kMaxGpl], BucketMeta& m) {
+                                                const BucketCtx& c, WORD (&w)[kMaxGpl], BucketMeta& m) {
   const uint32_t lane = threadIdx.x & 31u;
   m = load_meta(rec, bk);
   const uint8_t* pay = rec + meta_bytes;
 #pragma unroll
   for (int k = 0; k < kMaxGpl; ++k)
-    w[k] = (FULL || c.nv[k] > 0) ? load_group_word(pay, c.grp0 + (uint32_t)k * 32u + lane, bits) : 0ull;
+    w[k] = (FULL || c.nv[k] > 0) ? (WORD)load_group_word(pay, c.grp0 + (uint32_t)k * 32u + lane, bits) : (WORD)0;
 }
 
 // level j of a packed word; 32-bit arithmetic when the whole group fits in 32 bits
@@ -119,8 +120,8 @@ __device__ __forceinline__ uint32_t unpack_level(uint64_t w, int j, int bits) {
   return unpack1(w, j, bits);
 }
 
-template <bool FULL>
-__device__ __forceinline__ void warp_accumulate(const uint64_t (&w)[kMaxGpl], const BucketMeta& m, int bits,
+template <bool FULL, typename WORD>
+__device__ __forceinline__ void warp_accumulate(const WORD (&w)[kMaxGpl], const BucketMeta& m, int bits,
                                                 const BucketCtx& c, float (&x)[kMaxGpl][8]) {
 #pragma unroll
   for (int k = 0; k < kMaxGpl; ++k) {
@@ -251,7 +252,7 @@ __device__ __forceinline__ void warp_decode_store(const uint8_t* rec, uint32_t m
   const uint32_t lane = threadIdx.x & 31u;
   uint64_t w[kMaxGpl];
   BucketMeta m;
-  warp_fetch_peer<FULL>(rec, meta_bytes, bk, bits, c, w, m);
+  warp_fetch_peer<FULL, uint64_t>(rec, meta_bytes, bk, bits, c, w, m);
 #pragma unroll
   for (int k = 0; k < kMaxGpl; ++k) {
     if (!FULL && c.nv[k] == 0) continue;
