@@ -70,6 +70,8 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--bucket-size", type=int, default=512)
+    ap.add_argument("--with-nccl-sra", action="store_true",
+                    help="also time the reference-structure path: SRA over NCCL send/recv + separate kernels")
     args = ap.parse_args()
 
     rank, world, local = cgx.map_launcher_env()
@@ -81,6 +83,14 @@ def main():
     es = torch.empty((), dtype=dtype).element_size()
     os.environ["CGX_COMPRESSION_BUCKET_SIZE"] = str(args.bucket_size)
     be = cgx.get_backend()
+    nccl_sra = None
+    if args.with_nccl_sra:
+        # a second cgx group whose intra-node transport is NCCL send/recv with standalone
+        # quantize/dequantize kernels: the structure of the reference's NCCL_Reduce
+        # (/root/reference/src/common/nccl_reduce.cc:103-198), i.e. "a path that only calls NCCL"
+        os.environ["CGX_INNER_COMMUNICATOR_TYPE"] = "NCCL"
+        nccl_sra = dist.new_group(backend="cgx")
+        os.environ.pop("CGX_INNER_COMMUNICATOR_TYPE")
 
     sizes = []
     s = args.min_kb << 10
@@ -117,6 +127,15 @@ def main():
             rows.append(r)
             if rank == 0:
                 print(json.dumps(r), flush=True)
+            if nccl_sra is not None and bits < 32 and nbytes >= 4096:
+                t2 = time_allreduce(lambda x: dist.all_reduce(x, group=nccl_sra), bufs, iters, args.warmup, dev)
+                r = dict(row_base, impl="cgx_sra_over_nccl_sendrecv", bits=bits, time_us=round(t2, 2),
+                         algbw_gbs=round(nbytes / t2 / 1e3, 2),
+                         busbw_gbs=round(nbytes / t2 / 1e3 * 2 * (world - 1) / world, 2),
+                         speedup_vs_nccl=round(t_nccl / t2, 3), fused_speedup_over_this=round(t2 / t, 3))
+                rows.append(r)
+                if rank == 0:
+                    print(json.dumps(r), flush=True)
         del bufs
     if rank == 0:
         Path(args.out).parent.mkdir(parents=True, exist_ok=True)

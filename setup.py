@@ -22,6 +22,9 @@ SOURCES = [
     "common/sra_sim.cc",
     "comm/symmetric_heap.cc",
     "reduce/fused_sra.cc",
+    "reduce/block_backend.cc",
+    "reduce/reducers.cc",
+    "pg/c10d_communicator.cc",
     "engine/engine.cc",
     "kernels/sra_fused.cu",
     "kernels/quantize.cu",

@@ -27,13 +27,49 @@ def _create_backend(store, rank: int, size: int, timeout: timedelta):
     """
     cpu_delegate = None
     cuda_delegate = None
-    if dist.is_gloo_available():
-        cpu_delegate = dist.ProcessGroupGloo(dist.PrefixStore("cgx_gloo/", store), rank, size, timeout=timeout)
-    if torch.cuda.is_available() and dist.is_nccl_available():
+    have_cuda = torch.cuda.is_available() and dist.is_nccl_available()
+
+    def gloo(prefix: str, r: int, n: int):
+        return dist.ProcessGroupGloo(dist.PrefixStore(prefix, store), r, n, timeout=timeout)
+
+    def nccl(prefix: str, r: int, n: int):
         opts = dist.ProcessGroupNCCL.Options()
         opts._timeout = timeout
-        cuda_delegate = dist.ProcessGroupNCCL(dist.PrefixStore("cgx_nccl/", store), rank, size, opts)
-    return _C.create_backend(dist.PrefixStore("cgx_core/", store), rank, size, timeout, cpu_delegate, cuda_delegate)
+        return dist.ProcessGroupNCCL(dist.PrefixStore(prefix, store), r, n, opts)
+
+    if dist.is_gloo_available():
+        cpu_delegate = gloo("cgx_gloo/", rank, size)
+    if have_cuda:
+        cuda_delegate = nccl("cgx_nccl/", rank, size)
+
+    # topology: `local_size` consecutive ranks share a node (reference: MPI shared-memory split,
+    # /root/reference/src/common/mpi_context.cc:25-35). CGX_LOCAL_SIZE simulates several nodes on one box.
+    local_size = _local_size(size)
+    subs = dict(cpu_local=None, cpu_cross=None, cuda_local=None, cuda_cross=None)
+    if local_size < size:
+        node, lrank, nodes = rank // local_size, rank % local_size, size // local_size
+        if dist.is_gloo_available():
+            if local_size > 1:
+                subs["cpu_local"] = gloo(f"cgx_gloo_local{node}/", lrank, local_size)
+            subs["cpu_cross"] = gloo(f"cgx_gloo_cross{lrank}/", node, nodes)
+        if have_cuda:
+            if local_size > 1:
+                subs["cuda_local"] = nccl(f"cgx_nccl_local{node}/", lrank, local_size)
+            subs["cuda_cross"] = nccl(f"cgx_nccl_cross{lrank}/", node, nodes)
+    return _C.create_backend(dist.PrefixStore("cgx_core/", store), rank, size, timeout, cpu_delegate, cuda_delegate,
+                             local_size, subs["cpu_local"], subs["cpu_cross"], subs["cuda_local"], subs["cuda_cross"])
+
+
+def _local_size(world: int) -> int:
+    import os
+
+    for var in ("CGX_LOCAL_SIZE", "LOCAL_WORLD_SIZE"):
+        v = os.environ.get(var)
+        if v and v.isdigit():
+            n = int(v)
+            if 1 <= n <= world and world % n == 0:
+                return n
+    return world
 
 
 def register_backend() -> None:

@@ -244,9 +244,19 @@ class LocalSraGroup {
 c10::intrusive_ptr<c10d::Backend> create_backend(const c10::intrusive_ptr<c10d::Store>& store, int rank, int size,
                                                  const std::chrono::milliseconds& timeout,
                                                  c10::intrusive_ptr<c10d::Backend> cpu_delegate,
-                                                 c10::intrusive_ptr<c10d::Backend> cuda_delegate) {
+                                                 c10::intrusive_ptr<c10d::Backend> cuda_delegate, int local_size,
+                                                 c10::intrusive_ptr<c10d::Backend> cpu_local,
+                                                 c10::intrusive_ptr<c10d::Backend> cpu_cross,
+                                                 c10::intrusive_ptr<c10d::Backend> cuda_local,
+                                                 c10::intrusive_ptr<c10d::Backend> cuda_cross) {
+  ProcessGroupCGX::Topology topo;
+  topo.local_size = local_size;
+  topo.cpu_local = std::move(cpu_local);
+  topo.cpu_cross = std::move(cpu_cross);
+  topo.cuda_local = std::move(cuda_local);
+  topo.cuda_cross = std::move(cuda_cross);
   return c10::make_intrusive<ProcessGroupCGX>(store, rank, size, timeout, std::move(cpu_delegate),
-                                              std::move(cuda_delegate));
+                                              std::move(cuda_delegate), std::move(topo));
 }
 
 }  // namespace
@@ -261,6 +271,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("init_cuda", &ProcessGroupCGX::init_cuda, py::call_guard<py::gil_scoped_release>())
       .def("p2p_ready", &ProcessGroupCGX::p2p_ready)
       .def("lanes", &ProcessGroupCGX::lanes)
+      .def("local_size", &ProcessGroupCGX::local_size)
       .def("stats", &ProcessGroupCGX::stats)
       .def("reset_stats", &ProcessGroupCGX::reset_stats)
       .def("check_health", &ProcessGroupCGX::check_health)
@@ -268,7 +279,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("read_trace", &ProcessGroupCGX::read_trace);
 
   m.def("create_backend", &create_backend, py::arg("store"), py::arg("rank"), py::arg("size"), py::arg("timeout"),
-        py::arg("cpu_delegate"), py::arg("cuda_delegate"), py::call_guard<py::gil_scoped_release>());
+        py::arg("cpu_delegate"), py::arg("cuda_delegate"), py::arg("local_size") = 0,
+        py::arg("cpu_local") = nullptr, py::arg("cpu_cross") = nullptr, py::arg("cuda_local") = nullptr,
+        py::arg("cuda_cross") = nullptr, py::call_guard<py::gil_scoped_release>());
 
   // reference pybind surface
   m.def("register_layer", [](unsigned bucket_idx, unsigned layer_idx, int64_t numel, int bits, int bucket_size) {

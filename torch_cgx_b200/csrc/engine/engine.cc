@@ -40,11 +40,36 @@ std::vector<std::vector<LayerSpec>> split_for_fusion(const std::vector<LayerSpec
 }
 
 AllreduceEngine::AllreduceEngine(int rank, int world, const EngineConfig& cfg)
-    : rank_(rank), world_(world), cfg_(cfg) {}
+    : rank_(rank), world_(world), local_size_(world), cfg_(cfg) {}
 
 AllreduceEngine::~AllreduceEngine() {
+  // reducers release their scratch through the block backend: they must go first
+  for (GenericPath* g : {&gen_cuda_, &gen_cpu_}) {
+    g->cross.reset();
+    g->intra.reset();
+    g->cross_comm.reset();
+    g->intra_comm.reset();
+    g->ops.reset();
+  }
   fused_.reset();
   heap_.reset();
+}
+
+void AllreduceEngine::set_topology(int local_size) {
+  if (local_size < 1 || local_size > world_ || world_ % local_size != 0) local_size = world_;
+  local_size_ = local_size;
+}
+
+void AllreduceEngine::attach_generic(bool cuda, std::unique_ptr<Communicator> intra,
+                                     std::unique_ptr<Communicator> cross) {
+  GenericPath& g = cuda ? gen_cuda_ : gen_cpu_;
+  g.intra.reset();
+  g.cross.reset();
+  g.ops = cuda ? make_cuda_block_backend() : make_cpu_block_backend();
+  g.intra_comm = std::move(intra);
+  g.cross_comm = std::move(cross);
+  if (g.intra_comm) g.intra = make_reducer(cfg_.inner_reduction, g.intra_comm.get(), g.ops.get());
+  if (g.cross_comm) g.cross = make_reducer(cfg_.cross_reduction, g.cross_comm.get(), g.ops.get());
 }
 
 size_t AllreduceEngine::required_slot_bytes(const EngineConfig& cfg, int world) {
@@ -63,24 +88,104 @@ void AllreduceEngine::check_health() {
   if (fused_) fused_->check_status();
 }
 
+static std::vector<LayerSpec> resolve_layers(int64_t numel, const EngineConfig& cfg, const CompressionEnv& env,
+                                             int explicit_bucket) {
+  int64_t n_eff = numel;
+  if (cfg.fake_ratio < 1.0) n_eff = std::max<int64_t>(1, (int64_t)((double)numel * cfg.fake_ratio));
+  int resolved = -1;
+  return LayerRegistry::instance().extract(n_eff, env, cfg.min_compress_elems, explicit_bucket, &resolved);
+}
+
 void AllreduceEngine::allreduce_cuda(void* data, int dtype, int64_t numel, bool average, int explicit_bucket,
                                      cudaStream_t stream) {
   if (numel <= 0) return;
   CompressionEnv env = CompressionEnv::read();
-  int64_t n_eff = numel;
-  if (cfg_.fake_ratio < 1.0) n_eff = std::max<int64_t>(1, (int64_t)((double)numel * cfg_.fake_ratio));
-  int resolved = -1;
-  std::vector<LayerSpec> layers =
-      LayerRegistry::instance().extract(n_eff, env, cfg_.min_compress_elems, explicit_bucket, &resolved);
-  allreduce_cuda_layers(data, dtype, layers, average, env, stream);
+  allreduce_cuda_layers(data, dtype, resolve_layers(numel, cfg_, env, explicit_bucket), average, env, stream);
+}
+
+void AllreduceEngine::allreduce_cpu(void* data, int dtype, int64_t numel, bool average, int explicit_bucket) {
+  if (numel <= 0) return;
+  if (!gen_cpu_.ops) throw std::runtime_error("cgx: CPU reducers are not initialised");
+  CompressionEnv env = CompressionEnv::read();
+  run_layers(false, data, dtype, resolve_layers(numel, cfg_, env, explicit_bucket), average, env, nullptr);
 }
 
 void AllreduceEngine::allreduce_cuda_layers(void* data, int dtype, const std::vector<LayerSpec>& layers_in,
                                             bool average, const CompressionEnv& env, cudaStream_t stream) {
-  if (!fused_) throw std::runtime_error("cgx: P2P path is not initialised");
-  fused_->check_status();
-  std::vector<LayerSpec> layers = layers_in;
-  if (cfg_.dummy_compression || !cfg_.intra_compress)
+  const bool need_fused = cfg_.inner_comm == CommType::kP2P && local_size_ > 0;
+  if (need_fused && !fused_) throw std::runtime_error("cgx: P2P path is not initialised");
+  if (fused_) fused_->check_status();
+  run_layers(true, data, dtype, layers_in, average, env, stream);
+}
+
+// One node-local allreduce of a fusion group: fused P2P kernel when available,
+// otherwise the generic reducer over the intra-node communicator.
+void AllreduceEngine::intra_stage(bool cuda, void* data, int dtype, const std::vector<LayerSpec>& group,
+                                  bool skip_incomplete, float prescale, RngParams rng, cudaStream_t stream) {
+  GenericPath& g = cuda ? gen_cuda_ : gen_cpu_;
+  const int elsize = dtype_size(dtype);
+  if (cuda && fused_ && cfg_.inner_comm == CommType::kP2P) {
+    // work list; a group whose plan does not fit the heap slots is halved
+    std::vector<std::vector<LayerSpec>> todo{group};
+    uint32_t sub = 0;
+    while (!todo.empty()) {
+      std::vector<LayerSpec> gl = std::move(todo.back());
+      todo.pop_back();
+      const DevicePlan* dp = fused_->prepare(gl, dtype, skip_incomplete, stream);
+      if (dp == nullptr) {
+        if (gl.size() > 1) {
+          size_t half = gl.size() / 2;
+          std::vector<LayerSpec> a(gl.begin(), gl.begin() + half), b(gl.begin() + half, gl.end());
+          todo.push_back(std::move(b));
+          todo.push_back(std::move(a));
+        } else {
+          const LayerSpec& l = gl[0];
+          const uint64_t gran = (l.bits >= kRawBits) ? 512 : std::max<uint32_t>(1u, l.bucket);
+          if (l.numel <= gran)
+            throw std::runtime_error("cgx: fusion buffer too small for a single quantization bucket");
+          uint64_t h = std::max<uint64_t>(gran, (l.numel / 2) / gran * gran);
+          LayerSpec a = l, b = l;
+          a.numel = h;
+          b.elem_off = l.elem_off + h;
+          b.numel = l.numel - h;
+          todo.push_back({b});
+          todo.push_back({a});
+        }
+        continue;
+      }
+      RngParams r2 = rng;
+      r2.seq = (rng.seq << 3) | (sub++ & 7u);
+      fused_->run(*dp, data, prescale, r2, stream);
+      ++stats_.kernel_launches;
+      stats_.elements += dp->plan.numel;
+      const int lr = fused_->rank();
+      const int lw = fused_->world();
+      // bytes pushed by this rank: phase A = every chunk but mine, phase B = mine to W-1 peers
+      const uint64_t mine = dp->plan.chunk_wire_bytes[lr];
+      stats_.wire_bytes += (dp->plan.total_wire - mine) + mine * (uint64_t)(lw - 1);
+      const uint64_t my_elems = dp->plan.chunk_elems[lr];
+      stats_.raw_bytes += ((dp->plan.numel - my_elems) + my_elems * (uint64_t)(lw - 1)) * (uint64_t)elsize;
+    }
+    return;
+  }
+  if (g.intra) {
+    const uint64_t before = g.intra->bytes_sent();
+    g.intra->allreduce(data, dtype, group, skip_incomplete, prescale, rng, stream);
+    stats_.wire_bytes += g.intra->bytes_sent() - before;
+    uint64_t n = 0;
+    for (const LayerSpec& l : group) n += l.numel;
+    stats_.elements += n;
+    const int lw = local_size_;
+    stats_.raw_bytes += 2ull * n * (uint64_t)elsize * (uint64_t)(lw - 1) / (uint64_t)lw;
+    return;
+  }
+  if (local_size_ > 1) throw std::runtime_error("cgx: no intra-node reducer available for this tensor");
+}
+
+void AllreduceEngine::run_layers(bool cuda, void* data, int dtype, std::vector<LayerSpec> layers, bool average,
+                                 const CompressionEnv& env, cudaStream_t stream) {
+  GenericPath& g = cuda ? gen_cuda_ : gen_cpu_;
+  if (cfg_.dummy_compression)
     for (LayerSpec& l : layers) l.bits = kRawBits;
   const int elsize = dtype_size(dtype);
   const float prescale = average ? 1.0f / (float)world_ : 1.0f;
@@ -88,46 +193,36 @@ void AllreduceEngine::allreduce_cuda_layers(void* data, int dtype, const std::ve
   ++stats_.calls;
   RngParams rng;
   rng.seed = env.seed;
-  rng.seq = call_seq_;
   rng.stochastic = env.stochastic;
+  const bool multi_node = nodes() > 1;
+  if (multi_node && !g.cross) throw std::runtime_error("cgx: multi-node topology but no cross-node reducer");
 
-  // work list of layer groups; a group whose plan does not fit the heap slots is halved
-  std::vector<std::vector<LayerSpec>> todo = split_for_fusion(layers, elsize, cfg_.fusion_bytes);
-  std::reverse(todo.begin(), todo.end());
   uint32_t sub = 0;
-  while (!todo.empty()) {
-    std::vector<LayerSpec> g = std::move(todo.back());
-    todo.pop_back();
-    const DevicePlan* dp = fused_->prepare(g, dtype, env.skip_incomplete, stream);
-    if (dp == nullptr) {
-      if (g.size() > 1) {
-        size_t half = g.size() / 2;
-        std::vector<LayerSpec> a(g.begin(), g.begin() + half), b(g.begin() + half, g.end());
-        todo.push_back(std::move(b));
-        todo.push_back(std::move(a));
-      } else {
-        const LayerSpec& l = g[0];
-        const uint64_t gran = (l.bits >= kRawBits) ? 512 : std::max<uint32_t>(1u, l.bucket);
-        if (l.numel <= gran) throw std::runtime_error("cgx: fusion buffer too small for a single quantization bucket");
-        uint64_t h = std::max<uint64_t>(gran, (l.numel / 2) / gran * gran);
-        LayerSpec a = l, b = l;
-        a.numel = h;
-        b.elem_off = l.elem_off + h;
-        b.numel = l.numel - h;
-        todo.push_back({b});
-        todo.push_back({a});
+  for (std::vector<LayerSpec>& group : split_for_fusion(layers, elsize, cfg_.fusion_bytes)) {
+    rng.seq = (call_seq_ << 4) | (sub++ & 15u);
+    // ---- stage 1: inside the node (reference: mpi_allreduce_operations.cc:146-160)
+    std::vector<LayerSpec> intra_layers = group;
+    if (!cfg_.intra_compress && multi_node)
+      for (LayerSpec& l : intra_layers) l.bits = kRawBits;
+    if (local_size_ > 1 || !multi_node) intra_stage(cuda, data, dtype, intra_layers, env.skip_incomplete, prescale, rng, stream);
+    if (!multi_node) continue;
+    // ---- stage 2: across nodes (reference: mpi_allreduce_operations.cc:161-183)
+    RngParams crng = rng;
+    crng.seq = rng.seq ^ 0x40000000u;
+    const float cross_scale = (local_size_ > 1) ? 1.0f : prescale;
+    if (cfg_.intra_broadcast && local_size_ > 1) {
+      if (local_rank() == 0) g.cross->allreduce(data, dtype, group, env.skip_incomplete, cross_scale, crng, stream);
+      // leaders hand the result to the rest of their node (raw bytes of the group's span)
+      uint64_t lo = ~0ull, hi = 0;
+      for (const LayerSpec& l : group) {
+        lo = std::min<uint64_t>(lo, l.elem_off);
+        hi = std::max<uint64_t>(hi, l.elem_off + l.numel);
       }
-      continue;
+      if (hi > lo && g.intra)
+        g.intra->broadcast(static_cast<uint8_t*>(data) + lo * elsize, (size_t)(hi - lo) * elsize, 0, stream);
+    } else {
+      g.cross->allreduce(data, dtype, group, env.skip_incomplete, cross_scale, crng, stream);
     }
-    rng.seq = (call_seq_ << 6) | (sub++ & 63u);  // distinct random stream per sub-call
-    fused_->run(*dp, data, prescale, rng, stream);
-    ++stats_.kernel_launches;
-    stats_.elements += dp->plan.numel;
-    // bytes pushed by this rank: phase A = every chunk but mine, phase B = mine to W-1 peers
-    const uint64_t mine = dp->plan.chunk_wire_bytes[rank_];
-    stats_.wire_bytes += (dp->plan.total_wire - mine) + mine * (uint64_t)(world_ - 1);
-    const uint64_t my_elems = dp->plan.chunk_elems[rank_];
-    stats_.raw_bytes += ((dp->plan.numel - my_elems) + my_elems * (uint64_t)(world_ - 1)) * (uint64_t)elsize;
   }
 }
 

@@ -14,7 +14,10 @@
 #include "../comm/symmetric_heap.h"
 #include "../common/config.h"
 #include "../common/layers.h"
+#include "../comm/communicator.h"
+#include "../reduce/block_backend.h"
 #include "../reduce/fused_sra.h"
+#include "../reduce/reducers.h"
 
 namespace cgx {
 
@@ -34,10 +37,37 @@ struct EngineStats {
 std::vector<std::vector<LayerSpec>> split_for_fusion(const std::vector<LayerSpec>& layers, int elsize,
                                                      int64_t fusion_bytes);
 
+// Reducers of one memory kind (host or device): the generic intra-node and
+// cross-node stages of the hierarchical allreduce.
+struct GenericPath {
+  std::unique_ptr<BlockBackend> ops;
+  std::unique_ptr<Communicator> intra_comm;  // ranks of my node (null if the node has one rank)
+  std::unique_ptr<Communicator> cross_comm;  // ranks with my local rank on the other nodes (null if one node)
+  std::unique_ptr<Reducer> intra;
+  std::unique_ptr<Reducer> cross;
+};
+
 class AllreduceEngine {
  public:
   AllreduceEngine(int rank, int world, const EngineConfig& cfg);
   ~AllreduceEngine();
+
+  // Topology: `local_size` consecutive ranks form a node (reference: MPIContext's
+  // shared-memory split, /root/reference/src/common/mpi_context.cc:25-35;
+  // overridable with CGX_LOCAL_SIZE to simulate several nodes on one box).
+  void set_topology(int local_size);
+  int local_size() const { return local_size_; }
+  int local_rank() const { return rank_ % local_size_; }
+  int node() const { return rank_ / local_size_; }
+  int nodes() const { return world_ / local_size_; }
+
+  // Install the generic reducers for host (cuda == false) or device memory.
+  // Communicators may be null where the corresponding group has a single rank.
+  void attach_generic(bool cuda, std::unique_ptr<Communicator> intra, std::unique_ptr<Communicator> cross);
+  bool has_generic(bool cuda) const { return (cuda ? gen_cuda_ : gen_cpu_).ops != nullptr; }
+
+  // In-place SUM/AVG allreduce of a host buffer through the generic reducers.
+  void allreduce_cpu(void* data, int dtype, int64_t numel, bool average, int explicit_bucket);
 
   const EngineConfig& config() const { return cfg_; }
   int rank() const { return rank_; }
@@ -65,8 +95,15 @@ class AllreduceEngine {
   void reset_stats() { stats_ = EngineStats(); }
 
  private:
+  void run_layers(bool cuda, void* data, int dtype, std::vector<LayerSpec> layers, bool average,
+                  const CompressionEnv& env, cudaStream_t stream);
+  void intra_stage(bool cuda, void* data, int dtype, const std::vector<LayerSpec>& group, bool skip_incomplete,
+                   float prescale, RngParams rng, cudaStream_t stream);
+
   int rank_, world_;
+  int local_size_;
   EngineConfig cfg_;
+  GenericPath gen_cuda_, gen_cpu_;
   std::unique_ptr<SymmetricHeap> heap_;
   std::unique_ptr<FusedSra> fused_;
   uint32_t call_seq_ = 0;

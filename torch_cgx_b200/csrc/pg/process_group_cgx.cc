@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "../kernels/launch.h"
+#include "c10d_communicator.h"
 
 namespace cgx {
 
@@ -72,15 +73,31 @@ c10::intrusive_ptr<c10::ivalue::Future> WorkCGX::getFuture() { return future_; }
 ProcessGroupCGX::ProcessGroupCGX(const c10::intrusive_ptr<c10d::Store>& store, int rank, int size,
                                  std::chrono::milliseconds timeout,
                                  c10::intrusive_ptr<c10d::Backend> cpu_delegate,
-                                 c10::intrusive_ptr<c10d::Backend> cuda_delegate)
+                                 c10::intrusive_ptr<c10d::Backend> cuda_delegate, Topology topo)
     : c10d::Backend(rank, size),
       store_(store),
       timeout_(timeout),
       cpu_delegate_(std::move(cpu_delegate)),
       cuda_delegate_(std::move(cuda_delegate)),
+      topo_(std::move(topo)),
       cfg_(EngineConfig::read()) {
-  TORCH_CHECK(size >= 1 && size <= kMaxPeers || cfg_.inner_comm != CommType::kP2P,
+  compress_cpu_ = env_bool("CGX_COMPRESS_CPU", false);
+  engine_ = std::make_unique<AllreduceEngine>(rank, size, cfg_);
+  engine_->set_topology(topo_.local_size > 0 ? topo_.local_size : size);
+  TORCH_CHECK(engine_->local_size() <= kMaxPeers || cfg_.inner_comm != CommType::kP2P,
               "cgx: the P2P path supports at most ", kMaxPeers, " ranks per node");
+  // host-memory reducers (Gloo transport): whole group when single-node, else local + cross sub-groups
+  {
+    std::unique_ptr<Communicator> intra, cross;
+    if (engine_->nodes() > 1) {
+      if (topo_.cpu_local && engine_->local_size() > 1)
+        intra = std::make_unique<C10dCommunicator>(topo_.cpu_local, false, -1);
+      if (topo_.cpu_cross) cross = std::make_unique<C10dCommunicator>(topo_.cpu_cross, false, -1);
+    } else if (cpu_delegate_ && size > 1) {
+      intra = std::make_unique<C10dCommunicator>(cpu_delegate_, false, -1);
+    }
+    if (intra || cross || size == 1) engine_->attach_generic(false, std::move(intra), std::move(cross));
+  }
   log_msg(1, "cgx[%d/%d]: backend created (inner=%s/%s fusion=%lld MB lanes=%d)", rank, size,
           to_string(cfg_.inner_comm), to_string(cfg_.inner_reduction), (long long)(cfg_.fusion_bytes >> 20),
           cfg_.lanes);
@@ -90,8 +107,8 @@ ProcessGroupCGX::~ProcessGroupCGX() {
   if (engine_ && device_ >= 0) {
     c10::cuda::CUDAGuard g(device_);
     cudaDeviceSynchronize();
-    engine_.reset();
   }
+  engine_.reset();
 }
 
 c10::intrusive_ptr<c10d::Backend> ProcessGroupCGX::delegate_for(const at::Tensor& t, const char* op) {
@@ -105,19 +122,20 @@ c10::intrusive_ptr<c10d::Backend> ProcessGroupCGX::delegate_for(const at::Tensor
 
 bool ProcessGroupCGX::eligible_for_engine(const at::Tensor& t, const c10d::ReduceOp& op) const {
   // reference: do_compress = (fp16|fp32) && SUM && CUDA  (ProcessGroupCGX.cc:374-377); bf16 and AVG added
-  if (!t.is_cuda() || cfg_.inner_comm != CommType::kP2P) return false;
   if (to_cgx_dtype(t.scalar_type()) < 0) return false;
   if (!(op == c10d::ReduceOp::SUM || op == c10d::ReduceOp::AVG)) return false;
   if (!t.is_non_overlapping_and_dense()) return false;
-  if (getSize() > kMaxPeers) return false;
-  return true;
+  if (!t.is_cuda()) return compress_cpu_ && engine_->has_generic(false);
+  if (cfg_.inner_comm == CommType::kP2P) return true;
+  // NCCL transport (reference-structure path): needs a CUDA delegate to carry the bytes
+  return cuda_delegate_ != nullptr || getSize() == 1;
 }
 
 void ProcessGroupCGX::init_cuda(int64_t device_index) { ensure_cuda((c10::DeviceIndex)device_index); }
 
 void ProcessGroupCGX::ensure_cuda(c10::DeviceIndex dev) {
   std::lock_guard<std::mutex> lk(mu_);
-  if (engine_) {
+  if (cuda_ready_) {
     TORCH_CHECK(dev == device_, "cgx: this process group is bound to cuda:", (int)device_,
                 " but got a tensor on cuda:", (int)dev);
     return;
@@ -126,37 +144,51 @@ void ProcessGroupCGX::ensure_cuda(c10::DeviceIndex dev) {
   device_ = dev;
   comm_stream_ = c10::cuda::getStreamFromPool(/*isHighPriority=*/true, dev);
   start_event_.emplace(cudaEventDisableTiming);
-  auto engine = std::make_unique<AllreduceEngine>(getRank(), getSize(), cfg_);
+  const int lsize = engine_->local_size(), lrank = engine_->local_rank(), node = engine_->node();
 
-  // agree on the number of lanes (CTAs): min over ranks of what can be co-resident
-  int resident = sra_max_resident_ctas(kF32);
-  int sms = 0;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int want = cfg_.lanes > 0 ? cfg_.lanes : sms;
-  int mine = std::max(1, std::min(want, resident));
-  C10dKV kv(store_);
-  const std::string prefix = "cgx/p2p";
+  // device-memory generic reducers (NCCL send/recv transport): cross-node stage, intra-node
+  // broadcast in leader mode, and the whole intra-node stage when CGX_INNER_COMMUNICATOR_TYPE=NCCL
   {
-    std::vector<uint8_t> v(sizeof(int));
-    std::memcpy(v.data(), &mine, sizeof(int));
-    kv.set(prefix + "/lanes/" + std::to_string(getRank()), v);
+    std::unique_ptr<Communicator> intra, cross;
+    if (engine_->nodes() > 1) {
+      if (topo_.cuda_local && lsize > 1) intra = std::make_unique<C10dCommunicator>(topo_.cuda_local, true, dev);
+      if (topo_.cuda_cross) cross = std::make_unique<C10dCommunicator>(topo_.cuda_cross, true, dev);
+    } else if (cuda_delegate_ && getSize() > 1) {
+      intra = std::make_unique<C10dCommunicator>(cuda_delegate_, true, dev);
+    }
+    engine_->attach_generic(true, std::move(intra), std::move(cross));
   }
-  int lanes = mine;
-  for (int p = 0; p < getSize(); ++p) {
-    if (p == getRank()) continue;
-    auto v = kv.get(prefix + "/lanes/" + std::to_string(p));
-    int other = 0;
-    std::memcpy(&other, v.data(), sizeof(int));
-    lanes = std::min(lanes, other);
+
+  if (cfg_.inner_comm == CommType::kP2P) {
+    // agree on the number of lanes (CTAs): min over the node's ranks of what can be co-resident
+    int resident = sra_max_resident_ctas(kF32);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int want = cfg_.lanes > 0 ? cfg_.lanes : sms;
+    int mine = std::max(1, std::min(want, resident));
+    C10dKV kv(store_);
+    const std::string prefix = "cgx/p2p/node" + std::to_string(node);
+    {
+      std::vector<uint8_t> v(sizeof(int));
+      std::memcpy(v.data(), &mine, sizeof(int));
+      kv.set(prefix + "/lanes/" + std::to_string(lrank), v);
+    }
+    int lanes = mine;
+    for (int p = 0; p < lsize; ++p) {
+      if (p == lrank) continue;
+      auto v = kv.get(prefix + "/lanes/" + std::to_string(p));
+      int other = 0;
+      std::memcpy(&other, v.data(), sizeof(int));
+      lanes = std::min(lanes, other);
+    }
+    HeapLayout layout = HeapLayout::make(lsize, lanes, AllreduceEngine::required_slot_bytes(cfg_, lsize));
+    auto heap = std::make_unique<SymmetricHeap>(lrank, lsize, layout);
+    if (lsize > 1) heap->connect_ipc(kv, prefix);
+    engine_->attach_heap(std::move(heap), lanes);
+    log_msg(1, "cgx[%d]: P2P engine ready on cuda:%d (node %d, local %d/%d, lanes=%d, heap=%.1f MB, slot=%u B)",
+            getRank(), (int)dev, node, lrank, lsize, lanes, (double)layout.total / (1 << 20), layout.slot_bytes);
   }
-  HeapLayout layout =
-      HeapLayout::make(getSize(), lanes, AllreduceEngine::required_slot_bytes(cfg_, getSize()));
-  auto heap = std::make_unique<SymmetricHeap>(getRank(), getSize(), layout);
-  if (getSize() > 1) heap->connect_ipc(kv, prefix);
-  engine->attach_heap(std::move(heap), lanes);
-  engine_ = std::move(engine);
-  log_msg(1, "cgx[%d]: P2P engine ready on cuda:%d (lanes=%d, heap=%.1f MB, slot=%u B)", getRank(), (int)dev,
-          lanes, (double)layout.total / (1 << 20), layout.slot_bytes);
+  cuda_ready_ = true;
 }
 
 c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::engine_allreduce(at::Tensor& t, bool average, int bucket_idx) {
@@ -181,12 +213,26 @@ c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::engine_allreduce(at::Tensor& t, 
   return work;
 }
 
+c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::engine_allreduce_cpu(at::Tensor& t, bool average, int bucket_idx) {
+  // host tensors: synchronous in the caller's thread (the reference queues them to its worker
+  // thread, ProcessGroupCGX.cc:300-339; Gloo send/recv already overlap internally)
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    ++seq_;
+    engine_->allreduce_cpu(t.data_ptr(), to_cgx_dtype(t.scalar_type()), t.numel(), average, bucket_idx);
+  }
+  auto fut = c10::make_intrusive<c10::ivalue::Future>(c10::ListType::create(c10::TensorType::get()));
+  fut->markCompleted(at::IValue(std::vector<at::Tensor>{t}));
+  return c10d::Work::create_from_future(fut);
+}
+
 c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::allreduce(std::vector<at::Tensor>& tensors,
                                                           const c10d::AllreduceOptions& opts) {
   TORCH_CHECK(tensors.size() == 1, "cgx: allreduce expects exactly one tensor");
   at::Tensor& t = tensors[0];
   if (eligible_for_engine(t, opts.reduceOp)) {
-    return engine_allreduce(t, opts.reduceOp == c10d::ReduceOp::AVG, -1);
+    const bool avg = opts.reduceOp == c10d::ReduceOp::AVG;
+    return t.is_cuda() ? engine_allreduce(t, avg, -1) : engine_allreduce_cpu(t, avg, -1);
   }
   return delegate_for(t, "allreduce")->allreduce(tensors, opts);
 }
@@ -194,7 +240,9 @@ c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::allreduce(std::vector<at::Tensor
 c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::allreduce_bucket(at::Tensor& tensor, int64_t bucket_idx,
                                                                  bool average) {
   c10d::ReduceOp op = average ? c10d::ReduceOp::AVG : c10d::ReduceOp::SUM;
-  if (eligible_for_engine(tensor, op)) return engine_allreduce(tensor, average, (int)bucket_idx);
+  if (eligible_for_engine(tensor, op))
+    return tensor.is_cuda() ? engine_allreduce(tensor, average, (int)bucket_idx)
+                            : engine_allreduce_cpu(tensor, average, (int)bucket_idx);
   std::vector<at::Tensor> ts{tensor};
   c10d::AllreduceOptions o;
   if (average && !tensor.is_cuda()) {
@@ -318,7 +366,7 @@ c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::recvAnysource(std::vector<at::Te
 
 c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::barrier(const c10d::BarrierOptions& opts) {
   // A barrier must also drain this backend's own side stream.
-  if (engine_ && device_ >= 0) {
+  if (cuda_ready_ && device_ >= 0) {
     c10::cuda::CUDAGuard g(device_);
     comm_stream_->synchronize();
     engine_->check_health();

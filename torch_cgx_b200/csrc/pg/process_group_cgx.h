@@ -56,11 +56,20 @@ class WorkCGX : public c10d::Work {
   c10::intrusive_ptr<c10::ivalue::Future> future_;
 };
 
+// Delegates of the node-local and cross-node sub-groups (hierarchical allreduce);
+// all optional. `local_size` consecutive ranks form a node.
+struct CgxTopology {
+  int local_size = 0;  // 0 = whole group is one node
+  c10::intrusive_ptr<c10d::Backend> cpu_local, cpu_cross, cuda_local, cuda_cross;
+};
+
 class ProcessGroupCGX : public c10d::Backend {
  public:
+  using Topology = CgxTopology;
+
   ProcessGroupCGX(const c10::intrusive_ptr<c10d::Store>& store, int rank, int size,
                   std::chrono::milliseconds timeout, c10::intrusive_ptr<c10d::Backend> cpu_delegate,
-                  c10::intrusive_ptr<c10d::Backend> cuda_delegate);
+                  c10::intrusive_ptr<c10d::Backend> cuda_delegate, Topology topo = Topology());
   ~ProcessGroupCGX() override;
 
   const std::string getBackendName() const override { return "cgx"; }
@@ -121,6 +130,7 @@ class ProcessGroupCGX : public c10d::Backend {
   // force the lazy CUDA-side initialisation (heap allocation + IPC exchange)
   void init_cuda(int64_t device_index);
   bool p2p_ready() const { return engine_ && engine_->has_p2p(); }
+  int64_t local_size() const { return engine_ ? engine_->local_size() : getSize(); }
   int64_t lanes() const;
   std::vector<int64_t> stats() const;  // calls, kernel launches, elements, wire bytes, raw bytes
   void reset_stats();
@@ -133,12 +143,16 @@ class ProcessGroupCGX : public c10d::Backend {
   c10::intrusive_ptr<c10d::Backend> delegate_for(const at::Tensor& t, const char* op);
   bool eligible_for_engine(const at::Tensor& t, const c10d::ReduceOp& op) const;
   c10::intrusive_ptr<c10d::Work> engine_allreduce(at::Tensor& t, bool average, int bucket_idx);
+  c10::intrusive_ptr<c10d::Work> engine_allreduce_cpu(at::Tensor& t, bool average, int bucket_idx);
   void ensure_cuda(c10::DeviceIndex dev);
 
   c10::intrusive_ptr<c10d::Store> store_;
   std::chrono::milliseconds timeout_;
   c10::intrusive_ptr<c10d::Backend> cpu_delegate_;
   c10::intrusive_ptr<c10d::Backend> cuda_delegate_;
+  Topology topo_;
+  bool compress_cpu_ = false;  // CGX_COMPRESS_CPU: route CPU float tensors through the generic reducers
+  bool cuda_ready_ = false;
   EngineConfig cfg_;
   std::unique_ptr<AllreduceEngine> engine_;
   std::optional<c10::cuda::CUDAStream> comm_stream_;
