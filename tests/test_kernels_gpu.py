@@ -152,3 +152,32 @@ def test_fused_sra_large_buffer_many_lanes():
     torch.cuda.synchronize()
     g.check()
     assert torch.equal(gpu[0].cpu(), cpu[0]) and torch.equal(gpu[1].cpu(), cpu[1])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_oneshot_kernel_matches_cpu_oracle(world, dtype):
+    layers = [(0, 4099, 4, 512), (4099, 33, 32, 512), (4132, 60_001, 8, 64), (64_133, 7, 32, 512),
+              (64_140, 50_000, 4, 1024)]
+    n = 114_140
+    torch.manual_seed(world)
+    ins = [(torch.randn(n) * (r + 1)).to(dtype) for r in range(world)]
+    for average in (False, True):
+        cpu = [t.clone() for t in ins]
+        C.oneshot_simulate(cpu, layers, 8, average, False, False, 0, 1, 256)
+        g = C.LocalSraGroup(world, 8, 4 << 20, 5000, 256)
+        for _ in range(3):  # alternating one-shot regions
+            gpu = [t.to(dev()) for t in ins]
+            g.allreduce_oneshot(gpu, layers, average, False, False, 0, 1)
+            torch.cuda.synchronize()
+            g.check()
+            for r in range(world):
+                assert torch.equal(gpu[r].cpu(), cpu[r])
+        # interleave with the three-phase kernel on the same heap
+        gpu = [t.to(dev()) for t in ins]
+        g.allreduce(gpu, layers, average, False, False, 0, 1)
+        gpu = [t.to(dev()) for t in ins]
+        g.allreduce_oneshot(gpu, layers, average, False, False, 0, 1)
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(gpu[r].cpu(), cpu[r])

@@ -106,3 +106,27 @@ def test_stochastic_sra_ranks_identical_and_seeded():
         assert torch.equal(o, a[0])
     assert torch.equal(a[0], b[0])
     assert not torch.equal(a[0], c[0])
+
+
+def test_oneshot_oracle_properties():
+    # one quantization per contribution: exact on constants, error below SRA's two rounds
+    world, n = 4, 50_000
+    ins = [torch.full((n,), float(r + 1)) for r in range(world)]
+    outs = [t.clone() for t in ins]
+    C.oneshot_simulate(outs, [(0, n, 4, 512)], lanes=4)
+    for o in outs:
+        assert torch.equal(o, torch.full((n,), 10.0))
+    torch.manual_seed(5)
+    ins = [torch.randn(n) for _ in range(world)]
+    a = [t.clone() for t in ins]
+    b = [t.clone() for t in ins]
+    C.oneshot_simulate(a, [(0, n, 4, 512)], lanes=4)
+    C.sra_simulate(b, [(0, n, 4, 512)], lanes=4)
+    exact = sum(ins)
+    for o in a[1:]:
+        assert torch.equal(o, a[0])
+    assert (a[0] - exact).abs().mean() < (b[0] - exact).abs().mean()
+    # raw layers are summed exactly
+    c = [t.clone() for t in ins]
+    C.oneshot_simulate(c, [(0, n, 32, 512)], lanes=2)
+    assert torch.allclose(c[0], exact, atol=1e-5)

@@ -113,6 +113,21 @@ void py_sra_simulate(std::vector<at::Tensor> tensors, const std::vector<LayerTup
   sra_simulate(plan, bufs, average ? 1.0f / (float)W : 1.0f, make_rng(stochastic, seed, seq));
 }
 
+void py_oneshot_simulate(std::vector<at::Tensor> tensors, const std::vector<LayerTuple>& layers, int lanes,
+                         bool average, bool skip_incomplete, bool stochastic, uint64_t seed, uint32_t seq,
+                         int64_t min_lane_elems) {
+  TORCH_CHECK(!tensors.empty(), "need tensors");
+  const int W = (int)tensors.size();
+  const int dt = cgx_dtype(tensors[0]);
+  std::vector<void*> bufs;
+  for (auto& t : tensors) {
+    TORCH_CHECK(t.device().is_cpu() && t.is_contiguous() && cgx_dtype(t) == dt, "oneshot_simulate: CPU contiguous tensors");
+    bufs.push_back(t.data_ptr());
+  }
+  Plan plan = build_plan(to_layers(layers), make_opts(1, lanes, dt, skip_incomplete, min_lane_elems));
+  oneshot_simulate(plan, bufs, average ? 1.0f / (float)W : 1.0f, make_rng(stochastic, seed, seq));
+}
+
 // quantize `t` through the plan; returns uint8 wire tensor [world, row_bytes]
 at::Tensor py_quantize(const at::Tensor& t, const std::vector<LayerTuple>& layers, int world, int lanes,
                        bool skip_incomplete, float prescale, bool stochastic, uint64_t seed, uint32_t seq,
@@ -185,7 +200,7 @@ class LocalSraGroup {
   LocalSraGroup(int world, int lanes, int64_t slot_bytes, int64_t timeout_ms, int64_t min_lane_elems)
       : world_(world) {
     TORCH_CHECK(world >= 1 && world <= kMaxPeers, "bad world size");
-    HeapLayout layout = HeapLayout::make(world, lanes, (size_t)slot_bytes);
+    HeapLayout layout = HeapLayout::make(world, lanes, (size_t)slot_bytes, (size_t)slot_bytes);
     for (int r = 0; r < world; ++r) heaps_.push_back(std::make_unique<SymmetricHeap>(r, world, layout));
     std::vector<SymmetricHeap*> all;
     for (auto& h : heaps_) all.push_back(h.get());
@@ -197,8 +212,16 @@ class LocalSraGroup {
   }
 
   // in-place allreduce of W same-device tensors, one per virtual rank
+  void allreduce_oneshot(std::vector<at::Tensor> tensors, const std::vector<LayerTuple>& layers, bool average,
+                         bool skip_incomplete, bool stochastic, uint64_t seed, uint32_t seq) {
+    run(std::move(tensors), layers, average, skip_incomplete, stochastic, seed, seq, true);
+  }
   void allreduce(std::vector<at::Tensor> tensors, const std::vector<LayerTuple>& layers, bool average,
                  bool skip_incomplete, bool stochastic, uint64_t seed, uint32_t seq) {
+    run(std::move(tensors), layers, average, skip_incomplete, stochastic, seed, seq, false);
+  }
+  void run(std::vector<at::Tensor> tensors, const std::vector<LayerTuple>& layers, bool average,
+           bool skip_incomplete, bool stochastic, uint64_t seed, uint32_t seq, bool oneshot) {
     TORCH_CHECK((int)tensors.size() == world_, "need one tensor per virtual rank");
     const int dt = cgx_dtype(tensors[0]);
     auto specs = to_layers(layers);
@@ -210,14 +233,19 @@ class LocalSraGroup {
     for (int r = 0; r < world_; ++r) {
       TORCH_CHECK(tensors[r].is_cuda() && tensors[r].is_contiguous() && cgx_dtype(tensors[r]) == dt, "bad tensor");
       ready.block(streams_[r]);
-      plans[r] = fused_[r]->prepare(specs, dt, skip_incomplete, streams_[r].stream());
+      plans[r] = oneshot ? fused_[r]->prepare_oneshot(specs, dt, skip_incomplete, streams_[r].stream())
+                         : fused_[r]->prepare(specs, dt, skip_incomplete, streams_[r].stream());
       TORCH_CHECK(plans[r] != nullptr, "plan does not fit the heap slots (raise slot_bytes)");
     }
     // make sure every plan upload has landed before any virtual rank starts spinning
     for (int r = 0; r < world_; ++r) streams_[r].synchronize();
-    for (int r = 0; r < world_; ++r)
-      fused_[r]->run(*plans[r], tensors[r].data_ptr(), average ? 1.0f / (float)world_ : 1.0f, rng,
-                     streams_[r].stream());
+    for (int r = 0; r < world_; ++r) {
+      const float ps = average ? 1.0f / (float)world_ : 1.0f;
+      if (oneshot)
+        fused_[r]->run_oneshot(*plans[r], tensors[r].data_ptr(), ps, rng, streams_[r].stream());
+      else
+        fused_[r]->run(*plans[r], tensors[r].data_ptr(), ps, rng, streams_[r].stream());
+    }
     for (int r = 0; r < world_; ++r) {
       at::cuda::CUDAEvent done(cudaEventDisableTiming);
       done.record(streams_[r]);
@@ -357,6 +385,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sra_simulate", &py_sra_simulate, py::arg("tensors"), py::arg("layers"), py::arg("lanes") = 1,
         py::arg("average") = false, py::arg("skip_incomplete") = false, py::arg("stochastic") = false,
         py::arg("seed") = 0, py::arg("seq") = 0, py::arg("min_lane_elems") = 2048);
+  m.def("oneshot_simulate", &py_oneshot_simulate, py::arg("tensors"), py::arg("layers"), py::arg("lanes") = 1,
+        py::arg("average") = false, py::arg("skip_incomplete") = false, py::arg("stochastic") = false,
+        py::arg("seed") = 0, py::arg("seq") = 0, py::arg("min_lane_elems") = 2048);
   m.def("quantize", &py_quantize, py::arg("tensor"), py::arg("layers"), py::arg("world") = 1, py::arg("lanes") = 1,
         py::arg("skip_incomplete") = false, py::arg("prescale") = 1.0f, py::arg("stochastic") = false,
         py::arg("seed") = 0, py::arg("seq") = 0, py::arg("rank") = 0, py::arg("phase") = 0,
@@ -400,6 +431,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("allreduce", &LocalSraGroup::allreduce, py::arg("tensors"), py::arg("layers"), py::arg("average") = false,
            py::arg("skip_incomplete") = false, py::arg("stochastic") = false, py::arg("seed") = 0,
            py::arg("seq") = 0)
+      .def("allreduce_oneshot", &LocalSraGroup::allreduce_oneshot, py::arg("tensors"), py::arg("layers"),
+           py::arg("average") = false, py::arg("skip_incomplete") = false, py::arg("stochastic") = false,
+           py::arg("seed") = 0, py::arg("seq") = 0)
       .def("check", &LocalSraGroup::check)
       .def("lanes_used", &LocalSraGroup::lanes_used);
 

@@ -19,7 +19,7 @@ void cuda_check(cudaError_t e, const char* what) {
 
 static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-HeapLayout HeapLayout::make(int world, int max_lanes, size_t slot_bytes) {
+HeapLayout HeapLayout::make(int world, int max_lanes, size_t slot_bytes, size_t os_slot_bytes) {
   HeapLayout l;
   l.world = world;
   l.flag_stride = (uint32_t)round_up((size_t)(max_lanes < 1 ? 1 : max_lanes), 32);
@@ -29,7 +29,10 @@ HeapLayout HeapLayout::make(int world, int max_lanes, size_t slot_bytes) {
   l.flags2_off = flags_bytes;
   l.recv1_off = 2 * flags_bytes;
   l.recv2_off = l.recv1_off + (size_t)world * l.slot_bytes;
-  l.total = l.recv2_off + (size_t)world * l.slot_bytes;
+  l.os_slot_bytes = (uint32_t)round_up(os_slot_bytes, 256);
+  l.os_off[0] = l.recv2_off + (size_t)world * l.slot_bytes;
+  l.os_off[1] = l.os_off[0] + (size_t)world * l.os_slot_bytes;
+  l.total = l.os_off[1] + (size_t)world * l.os_slot_bytes;
   return l;
 }
 

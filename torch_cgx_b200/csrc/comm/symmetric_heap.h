@@ -1,6 +1,6 @@
 // Symmetric peer-mapped device heap: the B200 replacement for the reference's
 // three point-to-point transports. Every rank owns ONE cudaMalloc'ed region
-//   [flags1][flags2][recv1: W slots][recv2: W slots]
+//   [flags1][flags2][recv1: W slots][recv2: W slots][one-shot A: W slots][one-shot B: W slots]
 // and maps every peer's region into its own address space (CUDA IPC between
 // processes, plain pointers inside one process), so kernels move data with
 // ordinary ld/st over NVLink 5 / NVSwitch and signal with release/acquire
@@ -25,8 +25,9 @@ struct HeapLayout {
   int world = 1;
   uint32_t flag_stride = 0;  // lanes capacity (multiple of 32)
   uint32_t slot_bytes = 0;   // bytes per (source rank) slot, multiple of 256
-  size_t flags1_off = 0, flags2_off = 0, recv1_off = 0, recv2_off = 0, total = 0;
-  static HeapLayout make(int world, int max_lanes, size_t slot_bytes);
+  uint32_t os_slot_bytes = 0;  // per-source slot of the two one-shot regions
+  size_t flags1_off = 0, flags2_off = 0, recv1_off = 0, recv2_off = 0, os_off[2] = {0, 0}, total = 0;
+  static HeapLayout make(int world, int max_lanes, size_t slot_bytes, size_t os_slot_bytes = 0);
 };
 
 // Minimal key-value rendezvous (implemented over c10d::Store by the backend,
@@ -59,6 +60,7 @@ class SymmetricHeap {
   uint8_t* base(int peer) const { return bases_[peer]; }
   uint8_t* recv1(int peer) const { return bases_[peer] + layout_.recv1_off; }
   uint8_t* recv2(int peer) const { return bases_[peer] + layout_.recv2_off; }
+  uint8_t* oneshot(int peer, int parity) const { return bases_[peer] + layout_.os_off[parity & 1]; }
   uint32_t* flags1(int peer) const { return reinterpret_cast<uint32_t*>(bases_[peer] + layout_.flags1_off); }
   uint32_t* flags2(int peer) const { return reinterpret_cast<uint32_t*>(bases_[peer] + layout_.flags2_off); }
 

@@ -38,6 +38,7 @@ constexpr const char* kEnvTimeoutMs = "CGX_TIMEOUT_MS";             // device-si
 constexpr const char* kEnvLocalSize = "CGX_LOCAL_SIZE";             // ranks per node override (simulated multi-node)
 constexpr const char* kEnvLogLevel = "CGX_LOG_LEVEL";               // 0 silent, 1 info, 2 debug
 constexpr const char* kEnvMinLaneElems = "CGX_MIN_LANE_ELEMS";
+constexpr const char* kEnvOneshotMaxBytes = "CGX_ONESHOT_MAX_BYTES";  // messages up to this size take the one-shot kernel (0 = never)
 
 constexpr int kDefaultBits = 32;          // 32 == compression off
 constexpr int kDefaultBucketSize = 512;   // reference compressor.h:32
@@ -85,6 +86,7 @@ struct EngineConfig {
   int64_t timeout_ms = 30000;
   int local_size = 0;
   uint32_t min_lane_elems = 2048;
+  int64_t oneshot_max_bytes = 512 << 10;
   static EngineConfig read();
 };
 

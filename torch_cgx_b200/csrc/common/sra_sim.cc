@@ -27,6 +27,25 @@ void sra_simulate(const Plan& plan, const std::vector<void*>& bufs, float presca
   }
 }
 
+void oneshot_simulate(const Plan& plan, const std::vector<void*>& bufs, float prescale, const RngParams& rng) {
+  if (plan.world != 1) throw std::invalid_argument("oneshot_simulate: plan must have a single chunk");
+  const int W = (int)bufs.size();
+  std::vector<float> acc(kMaxBlockElems), tmp(kMaxBlockElems);
+  std::vector<uint8_t> rec(kMaxBlockElems * 4 + 64 + kMaxBlockBuckets * 8 + 64);
+  for (uint32_t b = 0; b < plan.blocks.size(); ++b) {
+    const BlockDesc& d = plan.blocks[b];
+    const uint32_t n = block_n(d);
+    for (uint32_t i = 0; i < n; ++i) acc[i] = 0.f;
+    for (int q = 0; q < W; ++q) {
+      cpu::load_block(bufs[q], plan.dtype, d, prescale, tmp.data());
+      cpu::quantize_block(tmp.data(), plan.dtype, d, rec.data(), make_rng_key(rng, q, 0), b);
+      cpu::decode_block_add(rec.data(), plan.dtype, d, acc.data());
+    }
+    for (int p = 0; p < W; ++p)
+      for (uint32_t i = 0; i < n; ++i) cpu::store_elem(bufs[p], plan.dtype, (uint64_t)d.elem_off + i, acc[i]);
+  }
+}
+
 void roundtrip_simulate(const Plan& plan, void* buf, float prescale, const RngParams& rng, int rank, int phase) {
   std::vector<float> acc(kMaxBlockElems);
   std::vector<uint8_t> rec(kMaxBlockElems * 4 + 64 + kMaxBlockBuckets * 8 + 64);

@@ -31,6 +31,10 @@ inline RngKey make_rng_key(const RngParams& r, int rank, int phase) {
 // bufs[r] = base pointer of rank r's tensor (dtype plan.dtype), reduced in place.
 void sra_simulate(const Plan& plan, const std::vector<void*>& bufs, float prescale, const RngParams& rng);
 
+// One-shot allreduce oracle: result = T( sum over ranks r (in order) of decode(Q_r(x_r * prescale)) ),
+// every contribution quantized exactly once; `plan` must be a single-chunk plan (world == 1).
+void oneshot_simulate(const Plan& plan, const std::vector<void*>& bufs, float prescale, const RngParams& rng);
+
 // Quantize->dequantize round trip of one rank's buffer through the plan's
 // blocks (what a single compression step does to the data); used by the Python
 // ops and the tests.

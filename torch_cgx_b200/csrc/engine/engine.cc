@@ -72,6 +72,12 @@ void AllreduceEngine::attach_generic(bool cuda, std::unique_ptr<Communicator> in
   if (g.cross_comm) g.cross = make_reducer(cfg_.cross_reduction, g.cross_comm.get(), g.ops.get());
 }
 
+size_t AllreduceEngine::required_oneshot_slot_bytes(const EngineConfig& cfg) {
+  if (cfg.oneshot_max_bytes <= 0) return 0;
+  // whole-buffer image: raw worst case + per-block padding + one block of slack
+  return (size_t)cfg.oneshot_max_bytes + (size_t)cfg.oneshot_max_bytes / 8 + (size_t)kMaxBlockElems * 4 + 4096;
+}
+
 size_t AllreduceEngine::required_slot_bytes(const EngineConfig& cfg, int world) {
   // a raw chunk of a full fusion buffer + slack for chunk imbalance (one block)
   // and per-block 16 B padding
@@ -125,6 +131,22 @@ void AllreduceEngine::intra_stage(bool cuda, void* data, int dtype, const std::v
   GenericPath& g = cuda ? gen_cuda_ : gen_cpu_;
   const int elsize = dtype_size(dtype);
   if (cuda && fused_ && cfg_.inner_comm == CommType::kP2P) {
+    // latency-bound messages: single-hop one-shot kernel
+    if (fused_->world() > 1 && cfg_.oneshot_max_bytes > 0) {
+      uint64_t n = 0;
+      for (const LayerSpec& l : group) n += l.numel;
+      if ((int64_t)(n * (uint64_t)elsize) <= cfg_.oneshot_max_bytes) {
+        const DevicePlan* dp = fused_->prepare_oneshot(group, dtype, skip_incomplete, stream);
+        if (dp != nullptr) {
+          fused_->run_oneshot(*dp, data, prescale, rng, stream);
+          ++stats_.kernel_launches;
+          stats_.elements += dp->plan.numel;
+          stats_.wire_bytes += dp->plan.total_wire * (uint64_t)(fused_->world() - 1);
+          stats_.raw_bytes += n * (uint64_t)elsize * (uint64_t)(fused_->world() - 1);
+          return;
+        }
+      }
+    }
     // work list; a group whose plan does not fit the heap slots is halved
     std::vector<std::vector<LayerSpec>> todo{group};
     uint32_t sub = 0;

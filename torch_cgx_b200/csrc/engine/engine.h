@@ -75,6 +75,7 @@ class AllreduceEngine {
 
   // slot size the symmetric heap needs for this config
   static size_t required_slot_bytes(const EngineConfig& cfg, int world);
+  static size_t required_oneshot_slot_bytes(const EngineConfig& cfg);
 
   // takes ownership of a connected heap and enables the fused P2P path
   void attach_heap(std::unique_ptr<SymmetricHeap> heap, int lanes);

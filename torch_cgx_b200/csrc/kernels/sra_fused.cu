@@ -176,7 +176,8 @@ __device__ __forceinline__ void trace_mark(unsigned long long* trace, int lane, 
 // phase A: my copy of one bucket of a peer's chunk -> quantize -> peer's slot
 template <typename T, bool FULL, int KB>
 __device__ __forceinline__ void bucket_send(const T* __restrict__ blk, bool aligned, const BlockDesc& d, uint32_t bk,
-                                            float prescale, const RngKey& rng, uint32_t b, uint8_t* rec) {
+                                            float prescale, const RngKey& rng, uint32_t b, uint8_t* const* recs,
+                                            int nrec) {
   const int bits = KB ? KB : block_bits(d);
   const uint32_t meta_bytes = block_meta_bytes(block_n(d), d.bucket);
   const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
@@ -189,14 +190,14 @@ __device__ __forceinline__ void bucket_send(const T* __restrict__ blk, bool alig
     warp_minmax_update<FULL>(x, c, mn, mx);
   }
   const BucketMeta m = warp_minmax_finish(mn, mx, bits);
-  warp_store_meta(m, bk, &rec, 1);
+  warp_store_meta(m, bk, recs, nrec);
   if (ns == 1) {
-    warp_quantize_store<T, false, FULL>(x, c, m, bits, meta_bytes, rng, b, &rec, 1, nullptr, false);
+    warp_quantize_store<T, false, FULL>(x, c, m, bits, meta_bytes, rng, b, recs, nrec, nullptr, false);
   } else {
     for (uint32_t sl = 0; sl < ns; ++sl) {
       c = make_slice_ctx(d, bk, sl);
       warp_load_bucket<T, FULL>(blk, aligned, c, prescale, x);
-      warp_quantize_store<T, false, FULL>(x, c, m, bits, meta_bytes, rng, b, &rec, 1, nullptr, false);
+      warp_quantize_store<T, false, FULL>(x, c, m, bits, meta_bytes, rng, b, recs, nrec, nullptr, false);
     }
   }
 }
@@ -355,9 +356,9 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
           const uint32_t nb = block_num_buckets(n, d.bucket);
           for (uint32_t bk = first; bk < nb; bk += kNumWarps) {
             if (bucket_is_full(d, bk, aligned))
-              bucket_send<T, true, KB>(blk, aligned, d, bk, p.prescale, rng, b, rec);
+              bucket_send<T, true, KB>(blk, aligned, d, bk, p.prescale, rng, b, &rec, 1);
             else
-              bucket_send<T, false, KB>(blk, aligned, d, bk, p.prescale, rng, b, rec);
+              bucket_send<T, false, KB>(blk, aligned, d, bk, p.prescale, rng, b, &rec, 1);
             item_done_a();
           }
           base += nb;
@@ -518,6 +519,222 @@ __global__ void __launch_bounds__(kSraThreads, kMinBlocks) sra_fused_warp_kernel
   trace_mark(p.trace, lane, 5);
 }
 
+
+// ===========================================================================
+// One-shot allreduce for small / latency-bound messages: ONE signalling hop.
+// Every rank quantizes its WHOLE buffer once and stores the packed image into a
+// dedicated slot of every rank (itself included); after one flag exchange every
+// rank decodes all W images in rank order and sums them in fp32. Replicas are
+// bit-identical (same bytes, same order) and each contribution is quantized
+// exactly once (no requantization round). Costs W/2 x the wire bytes of SRA,
+// which is irrelevant below ~1 MB where latency dominates. Raw layers travel
+// as T. (SURVEY.md build plan step 5: "one-shot (small, latency-bound)";
+// replaces the reference's tiny-tensor all-to-all, reducer.cc:35-94.)
+// ===========================================================================
+template <typename T, bool FULL, int KB>
+__device__ __forceinline__ void bucket_sum_recv(const uint8_t* const* src_rec, int W, T* __restrict__ blk,
+                                                bool aligned, const BlockDesc& d, uint32_t bk) {
+  const int bits = KB ? KB : block_bits(d);
+  const uint32_t meta_bytes = block_meta_bytes(block_n(d), d.bucket);
+  const uint32_t ns = div_up(bucket_count(d, bk), kSliceElems);
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t sl = 0; sl < ns; ++sl) {
+    const BucketCtx c = make_slice_ctx(d, bk, sl);
+    float x[kMaxGpl][8];
+#pragma unroll
+    for (int k = 0; k < kMaxGpl; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[k][j] = 0.f;
+    for (int q0 = 0; q0 < W; q0 += 2) {
+      uint64_t w[2][kMaxGpl];
+      BucketMeta pm[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (q0 + u < W) warp_fetch_peer<FULL, uint64_t>(src_rec[q0 + u], meta_bytes, bk, bits, c, w[u], pm[u]);
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (q0 + u < W) warp_accumulate<FULL, uint64_t>(w[u], pm[u], bits, c, x);
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxGpl; ++k) {
+      if (!FULL && c.nv[k] == 0) continue;
+      T* o = blk + c.e0 + ((uint32_t)k * 32u + lane) * 8u;
+      store_group_values<T>(o, x[k], FULL || (c.nv[k] == 8 && aligned), c.nv[k]);
+    }
+  }
+}
+
+// raw item: out = T( sum_q float(rec_q[i]) ) in rank order
+template <typename T>
+__device__ __forceinline__ void warp_sum_raw(const uint8_t* const* src_rec, int W, T* __restrict__ blk, bool aligned,
+                                             uint32_t n, uint32_t it) {
+  constexpr int V = RawCfg<T>::V, U = RawCfg<T>::U;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lo = it * kRawItemElems;
+  float f[U][V];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int k = 0; k < V; ++k) f[u][k] = 0.f;
+  for (int q = 0; q < W; ++q) {
+    uint4 pw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i0 = lo + ((uint32_t)u * 32u + lane) * V;
+      pw[u] = (i0 < n) ? ld_sys_v4(src_rec[q] + (size_t)i0 * sizeof(T)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float g[V];
+      unpack16<T>(pw[u], g);
+#pragma unroll
+      for (int k = 0; k < V; ++k) f[u][k] += g[k];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint32_t i0 = lo + ((uint32_t)u * 32u + lane) * V;
+    if (i0 < n) raw_store_own<T>(blk, aligned, n, i0, pack16<T>(f[u]));
+  }
+}
+
+template <typename T, int KB>
+__global__ void __launch_bounds__(kSraThreads, 1) oneshot_kernel(const SraParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Tile& tile = *reinterpret_cast<Tile*>(smem_raw);
+  __shared__ uint32_t s_total, s_done;
+  __shared__ int s_abort;
+  const int lane = blockIdx.x;
+  const int r = p.rank, W = p.world;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, wl = tid & 31u;
+  T* data = reinterpret_cast<T*>(p.data);
+  // the plan has ONE chunk (the whole buffer): this lane's blocks
+  const uint32_t b0 = p.lane_first[lane], b1 = p.lane_first[lane + 1];
+  if (tid == 0) {
+    uint32_t tot = 0;
+    for (uint32_t b = b0; b < b1; ++b) tot += block_items(p.blocks[b]);
+    s_total = tot;
+    s_done = 0;
+    s_abort = 0;
+  }
+  __syncthreads();
+  if (b0 == b1) return;
+  const uint32_t total = s_total;
+  RngKey rng = p.rng;
+  rng.stream = (uint32_t)r * 2u;
+
+  // ---- phase 1: my quantized image -> slot r of every rank (including mine)
+  {
+    uint8_t* dst[kMaxPeers];
+    auto item_done = [&]() {
+      __syncwarp();
+      uint32_t last = 0;
+      if (wl == 0) last = (atom_add_acq_rel_cta(&s_done, 1u) + 1u == total) ? 1u : 0u;
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last && wl < (uint32_t)W && (int)wl != r)
+        st_release_sys(p.flags1[wl] + (size_t)r * p.flag_stride + lane, p.epoch);
+    };
+    uint32_t base = 0;
+    for (uint32_t b = b0; b < b1; ++b) {
+      const BlockDesc d = p.blocks[b];
+      for (int q = 0; q < W; ++q) dst[q] = p.recv1[q] + (size_t)r * p.slot_bytes + d.wire_off;
+      const uint32_t n = block_n(d);
+      const T* blk = data + d.elem_off;
+      const bool aligned = (reinterpret_cast<uintptr_t>(blk) & 15u) == 0;
+      const uint32_t first = (warp - base) & (kNumWarps - 1);
+      if (block_is_raw(d)) {
+        const uint32_t ni = div_up(n, kRawItemElems);
+        for (uint32_t i = first; i < ni; i += kNumWarps) {
+          constexpr int V = RawCfg<T>::V, U = RawCfg<T>::U;
+          float f[U][V];
+          raw_load_own<T>(blk, aligned, n, i * kRawItemElems, p.prescale, f);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint32_t i0 = i * kRawItemElems + ((uint32_t)u * 32u + wl) * V;
+            if (i0 >= n) continue;
+            const uint4 packed = pack16<T>(f[u]);
+            for (int q = 0; q < W; ++q) st_v4(dst[q] + (size_t)i0 * sizeof(T), packed);
+          }
+          item_done();
+        }
+        base += ni;
+      } else if (block_is_fast(d)) {
+        const uint32_t nb = block_num_buckets(n, d.bucket);
+        for (uint32_t bk = first; bk < nb; bk += kNumWarps) {
+          if (bucket_is_full(d, bk, aligned))
+            bucket_send<T, true, KB>(blk, aligned, d, bk, p.prescale, rng, b, dst, W);
+          else
+            bucket_send<T, false, KB>(blk, aligned, d, bk, p.prescale, rng, b, dst, W);
+          item_done();
+        }
+        base += nb;
+      } else {
+        const int bits = block_bits(d);
+        load_block<T>(data, d, p.prescale, tile.acc);
+        __syncthreads();
+        compute_meta(tile.acc, n, d.bucket, bits, tile.meta, tile.inv);
+        __syncthreads();
+        pack_block<T, false>(tile.acc, d, tile.meta, tile.inv, tile.pay, rng, b, nullptr);
+        __syncthreads();
+        store_record(tile.meta, tile.pay, block_meta_bytes(n, d.bucket), block_payload_bytes(n, bits), dst, W);
+        __syncthreads();
+        if (warp == 0) item_done();
+      }
+    }
+  }
+
+  // ---- phase 2: wait for my own CTA's image and for the W-1 peers, then sum all W images
+  {
+    bool ok = true;
+    if (wl < (uint32_t)W && (int)wl != r) {
+      ok = wait_flag(p.flags1[r] + (size_t)wl * p.flag_stride + lane, p.epoch, p.timeout_ns);
+      if (!ok) {
+        s_abort = 1;
+        *p.status = kSraTimeoutPhase1 | (wl << 8) | ((uint32_t)lane << 16);
+      }
+    }
+    if (wl == 0) {  // other warps of this CTA wrote parts of my own slot
+      uint32_t spins = 0;
+      while (atom_add_acq_rel_cta(&s_done, 0u) < total)
+        if (++spins > (1u << 28)) break;
+    }
+    if (!__all_sync(0xffffffffu, ok)) return;
+    const uint8_t* src[kMaxPeers];
+    uint32_t base = 0;
+    for (uint32_t b = b0; b < b1; ++b) {
+      const BlockDesc d = p.blocks[b];
+      for (int q = 0; q < W; ++q) src[q] = p.recv1[r] + (size_t)q * p.slot_bytes + d.wire_off;
+      const uint32_t n = block_n(d);
+      T* blk = data + d.elem_off;
+      const bool aligned = (reinterpret_cast<uintptr_t>(blk) & 15u) == 0;
+      const uint32_t first = (warp - base) & (kNumWarps - 1);
+      if (block_is_raw(d)) {
+        const uint32_t ni = div_up(n, kRawItemElems);
+        for (uint32_t i = first; i < ni; i += kNumWarps) warp_sum_raw<T>(src, W, blk, aligned, n, i);
+        base += ni;
+      } else if (block_is_fast(d)) {
+        const uint32_t nb = block_num_buckets(n, d.bucket);
+        for (uint32_t bk = first; bk < nb; bk += kNumWarps) {
+          if (bucket_is_full(d, bk, aligned))
+            bucket_sum_recv<T, true, KB>(src, W, blk, aligned, d, bk);
+          else
+            bucket_sum_recv<T, false, KB>(src, W, blk, aligned, d, bk);
+        }
+        base += nb;
+      } else {
+        // slow block: fp32 accumulators in shared memory, all W images in rank order
+        for (uint32_t i = tid; i < n; i += blockDim.x) tile.acc[i] = 0.f;
+        __syncthreads();
+        for (int q = 0; q < W; ++q) decode_add<T>(src[q], d, tile.acc);
+        __syncthreads();
+        T* out = data + d.elem_off;
+        for (uint32_t i = tid; i < n; i += blockDim.x) out[i] = DT<T>::from_float(tile.acc[i]);
+        __syncthreads();
+      }
+    }
+  }
+}
+
 template <typename T>
 cudaError_t launch_t(const SraParams& p, cudaStream_t stream) {
   static bool configured[64] = {};
@@ -535,9 +752,20 @@ cudaError_t launch_t(const SraParams& p, cudaStream_t stream) {
                            (int)sizeof(Tile));                                                                \
   if (e != cudaSuccess) return e;
     CGX_SET_SMEM(0) CGX_SET_SMEM(2) CGX_SET_SMEM(4) CGX_SET_SMEM(8)
+#define CGX_SET_SMEM_OS(KB_)                                                                                        \
+  e = cudaFuncSetAttribute(oneshot_kernel<T, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile)); \
+  if (e != cudaSuccess) return e;
+    CGX_SET_SMEM_OS(0) CGX_SET_SMEM_OS(2) CGX_SET_SMEM_OS(4) CGX_SET_SMEM_OS(8)
     configured[dev & 63] = true;
   }
-  if (p.variant == 1) {
+  if (p.variant == 3) {
+    switch (p.uniform_bits) {
+      case 2: oneshot_kernel<T, 2><<<p.lanes, kSraThreads, sizeof(Tile), stream>>>(p); break;
+      case 4: oneshot_kernel<T, 4><<<p.lanes, kSraThreads, sizeof(Tile), stream>>>(p); break;
+      case 8: oneshot_kernel<T, 8><<<p.lanes, kSraThreads, sizeof(Tile), stream>>>(p); break;
+      default: oneshot_kernel<T, 0><<<p.lanes, kSraThreads, sizeof(Tile), stream>>>(p); break;
+    }
+  } else if (p.variant == 1) {
     sra_fused_kernel<T><<<p.lanes, kSraThreads, sizeof(Tile), stream>>>(p);
   } else {
 #define CGX_LAUNCH_WARP(KB_, PB_, MB_) \

@@ -181,7 +181,8 @@ void ProcessGroupCGX::ensure_cuda(c10::DeviceIndex dev) {
       std::memcpy(&other, v.data(), sizeof(int));
       lanes = std::min(lanes, other);
     }
-    HeapLayout layout = HeapLayout::make(lsize, lanes, AllreduceEngine::required_slot_bytes(cfg_, lsize));
+    HeapLayout layout = HeapLayout::make(lsize, lanes, AllreduceEngine::required_slot_bytes(cfg_, lsize),
+                                          AllreduceEngine::required_oneshot_slot_bytes(cfg_));
     auto heap = std::make_unique<SymmetricHeap>(lrank, lsize, layout);
     if (lsize > 1) heap->connect_ipc(kv, prefix);
     engine_->attach_heap(std::move(heap), lanes);

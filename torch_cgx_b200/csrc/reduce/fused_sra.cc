@@ -46,8 +46,19 @@ FusedSra::~FusedSra() {
 
 const DevicePlan* FusedSra::prepare(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
                                     cudaStream_t stream) {
+  return prepare_impl(layers, dtype, skip_incomplete, stream, world(), heap_->layout().slot_bytes);
+}
+
+const DevicePlan* FusedSra::prepare_oneshot(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
+                                            cudaStream_t stream) {
+  if (heap_->layout().os_slot_bytes == 0) return nullptr;
+  return prepare_impl(layers, dtype, skip_incomplete, stream, 1, heap_->layout().os_slot_bytes);
+}
+
+const DevicePlan* FusedSra::prepare_impl(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
+                                         cudaStream_t stream, int plan_world, uint32_t capacity) {
   PlanOptions opt;
-  opt.world = world();
+  opt.world = plan_world;
   opt.lanes = max_lanes_;
   opt.dtype = dtype;
   opt.skip_incomplete = skip_incomplete;
@@ -64,7 +75,7 @@ const DevicePlan* FusedSra::prepare(const std::vector<LayerSpec>& layers, int dt
       ub = (ub == -1 || ub == bb) ? bb : 0;
     }
     dp->uniform_bits = ub > 0 ? ub : 0;
-    if (dp->plan.max_chunk_wire <= heap_->layout().slot_bytes && !dp->plan.blocks.empty()) {
+    if (dp->plan.max_chunk_wire <= capacity && !dp->plan.blocks.empty()) {
       const size_t bb = dp->plan.blocks.size() * sizeof(BlockDesc);
       const size_t lb = dp->plan.lane_first.size() * sizeof(uint32_t);
       cuda_check(cudaMalloc((void**)&dp->d_blocks, bb), "cudaMalloc(plan blocks)");
@@ -79,11 +90,21 @@ const DevicePlan* FusedSra::prepare(const std::vector<LayerSpec>& layers, int dt
     it = cache_.emplace(key, std::move(dp)).first;
   }
   const DevicePlan* dp = it->second.get();
-  if (dp->plan.max_chunk_wire > heap_->layout().slot_bytes) return nullptr;
+  if (dp->plan.max_chunk_wire > capacity) return nullptr;
   return dp;
 }
 
 void FusedSra::run(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream) {
+  launch(dp, data, prescale, rng, stream, false);
+}
+
+void FusedSra::run_oneshot(const DevicePlan& dp, void* data, float prescale, const RngParams& rng,
+                           cudaStream_t stream) {
+  launch(dp, data, prescale, rng, stream, true);
+}
+
+void FusedSra::launch(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream,
+                      bool oneshot) {
   if (!heap_->connected()) throw std::runtime_error("cgx: symmetric heap is not connected");
   if (dp.plan.blocks.empty()) return;
   ++epoch_;
@@ -98,11 +119,13 @@ void FusedSra::run(const DevicePlan& dp, void* data, float prescale, const RngPa
   p.epoch = epoch_;
   p.prescale = prescale;
   p.rng = make_rng_key(rng, rank(), 0);
-  p.slot_bytes = heap_->layout().slot_bytes;
+  // one-shot calls alternate between two dedicated regions: a peer can be at most one call ahead
+  const int parity = oneshot ? (int)(oneshot_calls_++ & 1u) : 0;
+  p.slot_bytes = oneshot ? heap_->layout().os_slot_bytes : heap_->layout().slot_bytes;
   p.flag_stride = heap_->layout().flag_stride;
   for (int q = 0; q < kMaxPeers; ++q) {
     const bool valid = q < world();
-    p.recv1[q] = valid ? heap_->recv1(q) : nullptr;
+    p.recv1[q] = valid ? (oneshot ? heap_->oneshot(q, parity) : heap_->recv1(q)) : nullptr;
     p.recv2[q] = valid ? heap_->recv2(q) : nullptr;
     p.flags1[q] = valid ? heap_->flags1(q) : nullptr;
     p.flags2[q] = valid ? heap_->flags2(q) : nullptr;
@@ -120,7 +143,7 @@ void FusedSra::run(const DevicePlan& dp, void* data, float prescale, const RngPa
     p.trace = d_trace_;
   }
   last_lanes_ = dp.plan.lanes;
-  p.variant = variant_;
+  p.variant = oneshot ? 3 : variant_;
   p.uniform_bits = dp.uniform_bits;
   cuda_check(launch_sra_fused(p, stream), "launch_sra_fused");
   ++launches_;

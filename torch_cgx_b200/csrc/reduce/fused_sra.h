@@ -43,6 +43,12 @@ class FusedSra {
   // in the same order (epoch counter).
   void run(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream);
 
+  // One-shot variant (single signalling hop, for latency-bound messages): plan over the WHOLE
+  // buffer (one chunk); nullptr if its packed image does not fit the heap's one-shot slots.
+  const DevicePlan* prepare_oneshot(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
+                                    cudaStream_t stream);
+  void run_oneshot(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream);
+
   // throws std::runtime_error if a kernel reported a timeout
   void check_status();
 
@@ -66,6 +72,11 @@ class FusedSra {
   unsigned long long* d_trace_ = nullptr;
   bool trace_on_ = false;
   int last_lanes_ = 0;
+  uint32_t oneshot_calls_ = 0;
+  const DevicePlan* prepare_impl(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
+                                 cudaStream_t stream, int plan_world, uint32_t capacity);
+  void launch(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream,
+              bool oneshot);
   std::unordered_map<uint64_t, std::unique_ptr<DevicePlan>> cache_;
 };
 
