@@ -109,7 +109,7 @@ EngineConfig EngineConfig::read() {
   c.timeout_ms = std::max<int64_t>(1, env_int(kEnvTimeoutMs, 30000));
   c.local_size = (int)env_int(kEnvLocalSize, 0);
   c.min_lane_elems = (uint32_t)std::max<int64_t>(8, env_int(kEnvMinLaneElems, 2048));
-  c.oneshot_max_bytes = std::max<int64_t>(0, env_int(kEnvOneshotMaxBytes, 512 << 10));
+  c.oneshot_max_bytes = std::max<int64_t>(0, env_int(kEnvOneshotMaxBytes, 2 << 20));
   return c;
 }
 

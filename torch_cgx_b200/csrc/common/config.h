@@ -86,7 +86,7 @@ struct EngineConfig {
   int64_t timeout_ms = 30000;
   int local_size = 0;
   uint32_t min_lane_elems = 2048;
-  int64_t oneshot_max_bytes = 512 << 10;
+  int64_t oneshot_max_bytes = 2 << 20;
   static EngineConfig read();
 };
 

@@ -137,7 +137,8 @@ void AllreduceEngine::intra_stage(bool cuda, void* data, int dtype, const std::v
       for (const LayerSpec& l : group) n += l.numel;
       if ((int64_t)(n * (uint64_t)elsize) <= cfg_.oneshot_max_bytes) {
         const DevicePlan* dp = fused_->prepare_oneshot(group, dtype, skip_incomplete, stream);
-        if (dp != nullptr) {
+        // every rank pushes its whole packed image to W-1 peers: keep that egress small
+        if (dp != nullptr && dp->plan.total_wire * (uint64_t)(fused_->world() - 1) <= (4ull << 20)) {
           fused_->run_oneshot(*dp, data, prescale, rng, stream);
           ++stats_.kernel_launches;
           stats_.elements += dp->plan.numel;
