@@ -121,3 +121,16 @@ def test_launcher_env_mapping(monkeypatch):
     monkeypatch.setenv("OMPI_COMM_WORLD_LOCAL_RANK", "3")
     assert cgx.map_launcher_env() == (3, 8, 3)
     assert os.environ["MASTER_ADDR"] == "127.0.0.1" and os.environ["MASTER_PORT"] == "4040"
+
+
+def test_bench_reference_arm_reports_unavailable():
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference"], capture_output=True, text=True)
+    assert out.returncode == 0
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and "unavailable" in d
