@@ -314,7 +314,7 @@ def main():
             "gpu_launches": int(launches),
             "e2e": e2e,
             "clocks": clocks,
-            "final_loss": round(float(last_loss), 4) if last_loss is not None else None,
+            "final_loss": round(float(last_loss.detach()), 4) if last_loss is not None else None,
         }
         print(json.dumps(out), flush=True)
     dist.destroy_process_group()
