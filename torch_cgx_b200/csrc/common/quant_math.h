@@ -74,7 +74,7 @@ CGX_HD BucketMeta make_meta(float mn, float mx, int bits) {
 // exactness test relies on, /root/reference/test/test_cgx.py:69-78).
 CGX_HD float inv_unit(float unit) {
 #if defined(__CUDA_ARCH__)
-  return unit < kQuantEps ? 0.f : __fdiv_rn(1.0f, unit);
+  return unit < kQuantEps ? 0.f : __frcp_rn(unit);  // correctly rounded == 1.0f / unit
 #else
   return unit < kQuantEps ? 0.f : 1.0f / unit;
 #endif

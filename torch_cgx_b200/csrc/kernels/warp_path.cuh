@@ -145,12 +145,22 @@ __device__ __forceinline__ void warp_minmax_update(const float (&x)[kMaxGpl][8],
   }
 }
 
+// Warp-wide min/max with ONE redux.sync each instead of 5 shuffle rounds: floats are mapped to
+// order-preserving signed integers (-0 < +0, like min.f32/max.f32); NaN is handled by a vote so
+// that it still poisons the bucket exactly like the NaN-propagating scalar path.
+__device__ __forceinline__ int float_to_ordered(float f) {
+  const int b = __float_as_int(f);
+  return b ^ ((b >> 31) & 0x7FFFFFFF);
+}
+__device__ __forceinline__ float ordered_to_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7FFFFFFF)); }
+
 __device__ __forceinline__ BucketMeta warp_minmax_finish(float mn, float mx, int bits) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
+  const bool has_nan = __any_sync(0xffffffffu, (mn != mn) || (mx != mx));
+  const int kmn = __reduce_min_sync(0xffffffffu, float_to_ordered(mn));
+  const int kmx = __reduce_max_sync(0xffffffffu, float_to_ordered(mx));
+  mn = ordered_to_float(kmn);
+  mx = ordered_to_float(kmx);
+  if (has_nan) mn = mx = __int_as_float(0x7fffffff);
   return make_meta(mn, mx, bits);
 }
 
