@@ -47,6 +47,8 @@ def parse_args():
     p.add_argument("--layer-min-size", type=int, default=1024)
     p.add_argument("--stochastic", type=int, default=-1)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--hook", default="native", choices=["native", "python"],
+                   help="native: C++ comm hook on the DDP reducer (default); python: cgx_hook as in the reference")
     return p.parse_args()
 
 
@@ -187,7 +189,10 @@ def main():
     if args.backend == "cgx":
         state = cgx.CGXState(None, layer_min_size=args.layer_min_size,
                              compression_params={"bits": bits, "bucket_size": args.bucket_size})
-        ddp.register_comm_hook(state, cgx.cgx_hook)
+        if args.hook == "native":
+            cgx.register_cgx_hook(ddp, state)
+        else:
+            ddp.register_comm_hook(state, cgx.cgx_hook)
     if is_lm:
         opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4, fused=True)
     else:
@@ -310,6 +315,7 @@ def main():
                 "optimizer": "AdamW(fused)" if is_lm else "SGD(momentum)", "grad_dtype": "fp32",
                 "l2": "inputs larger than L2: per-step working set (activations+weights+grads) is GBs >> 126 MB L2",
                 "lanes": native.lanes() if native is not None else None,
+                "hook": args.hook if args.backend == "cgx" else None,
             },
             "gpu_launches": int(launches),
             "e2e": e2e,

@@ -25,6 +25,7 @@ SOURCES = [
     "reduce/block_backend.cc",
     "reduce/reducers.cc",
     "pg/c10d_communicator.cc",
+    "pg/comm_hook.cc",
     "engine/engine.cc",
     "kernels/sra_fused.cu",
     "kernels/quantize.cu",

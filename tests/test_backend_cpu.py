@@ -98,3 +98,48 @@ def _ddp_cpu(rank, world):
 
 def test_ddp_hook_cpu_world2():
     spawn(_ddp_cpu, 2)
+
+
+def _ddp_cpu_native_hook(rank, world):
+    import torch_cgx_b200 as cgx
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    dist.init_process_group("cgx", init_method="env://", rank=rank, world_size=world)
+    try:
+        def make():
+            torch.manual_seed(0)
+            return torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.ReLU(), torch.nn.Linear(128, 10))
+
+        def train(use_native):
+            cgx.reset_layers()
+            ddp = DDP(make())
+            state = cgx.CGXState(None, layer_min_size=16, compression_params={"bits": 4, "bucket_size": 64})
+            handle = None
+            if use_native:
+                handle = cgx.register_cgx_hook(ddp, state)
+                assert handle is not None
+            else:
+                ddp.register_comm_hook(state, cgx.cgx_hook)
+            opt = torch.optim.SGD(ddp.parameters(), lr=0.1)
+            for step in range(5):
+                torch.manual_seed(100 + step * world + rank)
+                x, y = torch.randn(8, 64), torch.randint(0, 10, (8,))
+                opt.zero_grad()
+                torch.nn.functional.cross_entropy(ddp(x), y).backward()
+                opt.step()
+            steps = handle.step if handle is not None else state.step
+            return torch.cat([p.detach().reshape(-1) for p in ddp.parameters()]), steps
+
+        w_py, s_py = train(False)
+        layers_py = cgx._C.registered_bucket(0)
+        w_cc, s_cc = train(True)
+        assert s_py == s_cc == 5
+        assert cgx._C.registered_bucket(0) == layers_py  # same layer table (biases uncompressed)
+        assert torch.equal(w_py, w_cc)                   # identical training trajectory
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_native_cpp_hook_matches_python_hook():
+    spawn(_ddp_cpu_native_hook, 2)

@@ -109,7 +109,7 @@ def test_reference_suite_two_gpus():
     spawn(_reference_suite, 2, timeout=600)
 
 
-def _ddp_gpu(rank, world):
+def _ddp_gpu(rank, world, hook="python"):
     import torch_cgx_b200 as cgx
     from cgx_utils import CGXState, cgx_hook
     from torch.nn.parallel import DistributedDataParallel as DDP
@@ -123,7 +123,10 @@ def _ddp_gpu(rank, world):
         model = resnet18(num_classes=10, cifar_stem=True).cuda()
         ddp = DDP(model, device_ids=[rank])
         state = CGXState(None, layer_min_size=1024, compression_params={"bits": 4, "bucket_size": 512})
-        ddp.register_comm_hook(state, cgx_hook)
+        if hook == "native":
+            assert cgx.register_cgx_hook(ddp, state) is not None
+        else:
+            ddp.register_comm_hook(state, cgx_hook)
         opt = torch.optim.SGD(ddp.parameters(), lr=0.05, momentum=0.9)
         losses = []
         torch.manual_seed(1234 + rank)
@@ -156,8 +159,9 @@ def test_reference_suite_all_gpus():
 
 
 @pytest.mark.multigpu
-def test_ddp_hook_two_gpus():
-    spawn(_ddp_gpu, 2, timeout=600)
+@pytest.mark.parametrize("hook", ["python", "native"])
+def test_ddp_hook_two_gpus(hook):
+    spawn(_ddp_gpu, 2, args=(hook,), timeout=600)
 
 
 def _nccl_transport(rank, world):

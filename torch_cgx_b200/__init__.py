@@ -27,7 +27,7 @@ from .backend import (  # noqa: E402
     set_quantization_bits,
     set_quantization_bucket_size,
 )
-from .parallel.hooks import CGXState, cgx_hook  # noqa: E402
+from .parallel.hooks import CGXState, cgx_hook, register_cgx_hook  # noqa: E402
 from .utils.launch import map_launcher_env  # noqa: E402
 from . import models, ops, utils  # noqa: E402,F401
 
@@ -40,6 +40,7 @@ __all__ = [
     "get_backend",
     "map_launcher_env",
     "register_backend",
+    "register_cgx_hook",
     "register_layer",
     "reset_layers",
     "set_quantization_bits",

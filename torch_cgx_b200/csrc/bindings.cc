@@ -22,6 +22,7 @@
 #include "common/plan.h"
 #include "common/sra_sim.h"
 #include "kernels/launch.h"
+#include "pg/comm_hook.h"
 #include "pg/process_group_cgx.h"
 
 namespace py = pybind11;
@@ -305,6 +306,20 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("check_health", &ProcessGroupCGX::check_health)
       .def("enable_trace", &ProcessGroupCGX::enable_trace)
       .def("read_trace", &ProcessGroupCGX::read_trace);
+
+  py::class_<HookState, std::shared_ptr<HookState>>(m, "NativeHookState")
+      .def_property_readonly("step", [](const HookState& h) { return h.step.load(); })
+      .def_readonly("layer_min_size", &HookState::layer_min_size)
+      .def_readonly("bits", &HookState::bits)
+      .def_readonly("bucket_size", &HookState::bucket_size)
+      .def_readonly("register_step", &HookState::register_step);
+  m.def("register_native_hook",
+        [](const std::shared_ptr<c10d::Reducer>& reducer, const c10::intrusive_ptr<ProcessGroupCGX>& pg,
+           int64_t layer_min_size, int bits, int bucket_size, int register_step) {
+          return register_native_hook(reducer, pg, layer_min_size, bits, bucket_size, register_step);
+        },
+        py::arg("reducer"), py::arg("backend"), py::arg("layer_min_size"), py::arg("bits"), py::arg("bucket_size"),
+        py::arg("register_step") = 2);
 
   m.def("create_backend", &create_backend, py::arg("store"), py::arg("rank"), py::arg("size"), py::arg("timeout"),
         py::arg("cpu_delegate"), py::arg("cuda_delegate"), py::arg("local_size") = 0,

@@ -102,10 +102,74 @@ static std::vector<LayerSpec> resolve_layers(int64_t numel, const EngineConfig& 
   return LayerRegistry::instance().extract(n_eff, env, cfg.min_compress_elems, explicit_bucket, &resolved);
 }
 
+void AllreduceEngine::launch_fused(const Launch& l, void* data, float prescale, RngParams rng, cudaStream_t stream) {
+  const int elsize = dtype_size(l.dp->plan.dtype);
+  rng.seq = (rng.seq << 3) | (l.rng_sub & 7u);
+  const int lw = fused_->world(), lr = fused_->rank();
+  if (l.oneshot) {
+    fused_->run_oneshot(*l.dp, data, prescale, rng, stream);
+    stats_.wire_bytes += l.dp->plan.total_wire * (uint64_t)(lw - 1);
+    stats_.raw_bytes += l.dp->plan.numel * (uint64_t)elsize * (uint64_t)(lw - 1);
+  } else {
+    fused_->run(*l.dp, data, prescale, rng, stream);
+    // bytes pushed by this rank: phase A = every chunk but mine, phase B = mine to W-1 peers
+    const uint64_t mine = l.dp->plan.chunk_wire_bytes[lr];
+    stats_.wire_bytes += (l.dp->plan.total_wire - mine) + mine * (uint64_t)(lw - 1);
+    const uint64_t my_elems = l.dp->plan.chunk_elems[lr];
+    stats_.raw_bytes += ((l.dp->plan.numel - my_elems) + my_elems * (uint64_t)(lw - 1)) * (uint64_t)elsize;
+  }
+  ++stats_.kernel_launches;
+  stats_.elements += l.dp->plan.numel;
+  if (recording_) recording_->push_back(l);
+}
+
 void AllreduceEngine::allreduce_cuda(void* data, int dtype, int64_t numel, bool average, int explicit_bucket,
                                      cudaStream_t stream) {
   if (numel <= 0) return;
   CompressionEnv env = CompressionEnv::read();
+  const bool cacheable = explicit_bucket >= 0 && explicit_bucket < 4096 && nodes() == 1 && fused_ &&
+                         cfg_.inner_comm == CommType::kP2P && !cfg_.dummy_compression && cfg_.fake_ratio >= 1.0;
+  if (cacheable) {
+    if ((size_t)explicit_bucket >= fast_.size()) fast_.resize((size_t)explicit_bucket + 1);
+    BucketFast& f = fast_[(size_t)explicit_bucket];
+    const uint64_t ver = LayerRegistry::instance().version();
+    if (f.registry_version == ver && f.numel == numel && f.dtype == dtype && f.env_bits == env.bits &&
+        f.env_bucket == env.bucket_size && f.skip_incomplete == env.skip_incomplete && !f.launches.empty()) {
+      fused_->check_status();
+      ++call_seq_;
+      ++stats_.calls;
+      RngParams rng;
+      rng.seed = env.seed;
+      rng.stochastic = env.stochastic;
+      const float prescale = average ? 1.0f / (float)world_ : 1.0f;
+      uint32_t sub = 0;
+      const DevicePlan* prev_group = nullptr;
+      (void)prev_group;
+      for (const Launch& l : f.launches) {
+        rng.seq = (call_seq_ << 4) | ((sub++) & 15u);
+        launch_fused(l, data, prescale, rng, stream);
+      }
+      return;
+    }
+    // slow path once, recording what was launched
+    std::vector<Launch> rec;
+    recording_ = &rec;
+    try {
+      allreduce_cuda_layers(data, dtype, resolve_layers(numel, cfg_, env, explicit_bucket), average, env, stream);
+    } catch (...) {
+      recording_ = nullptr;
+      throw;
+    }
+    recording_ = nullptr;
+    f.registry_version = ver;
+    f.numel = numel;
+    f.dtype = dtype;
+    f.env_bits = env.bits;
+    f.env_bucket = env.bucket_size;
+    f.skip_incomplete = env.skip_incomplete;
+    f.launches = std::move(rec);
+    return;
+  }
   allreduce_cuda_layers(data, dtype, resolve_layers(numel, cfg_, env, explicit_bucket), average, env, stream);
 }
 
@@ -139,11 +203,7 @@ void AllreduceEngine::intra_stage(bool cuda, void* data, int dtype, const std::v
         const DevicePlan* dp = fused_->prepare_oneshot(group, dtype, skip_incomplete, stream);
         // every rank pushes its whole packed image to W-1 peers: keep that egress small
         if (dp != nullptr && dp->plan.total_wire * (uint64_t)(fused_->world() - 1) <= (4ull << 20)) {
-          fused_->run_oneshot(*dp, data, prescale, rng, stream);
-          ++stats_.kernel_launches;
-          stats_.elements += dp->plan.numel;
-          stats_.wire_bytes += dp->plan.total_wire * (uint64_t)(fused_->world() - 1);
-          stats_.raw_bytes += n * (uint64_t)elsize * (uint64_t)(fused_->world() - 1);
+          launch_fused(Launch{dp, true, 0u}, data, prescale, rng, stream);
           return;
         }
       }
@@ -176,18 +236,7 @@ void AllreduceEngine::intra_stage(bool cuda, void* data, int dtype, const std::v
         }
         continue;
       }
-      RngParams r2 = rng;
-      r2.seq = (rng.seq << 3) | (sub++ & 7u);
-      fused_->run(*dp, data, prescale, r2, stream);
-      ++stats_.kernel_launches;
-      stats_.elements += dp->plan.numel;
-      const int lr = fused_->rank();
-      const int lw = fused_->world();
-      // bytes pushed by this rank: phase A = every chunk but mine, phase B = mine to W-1 peers
-      const uint64_t mine = dp->plan.chunk_wire_bytes[lr];
-      stats_.wire_bytes += (dp->plan.total_wire - mine) + mine * (uint64_t)(lw - 1);
-      const uint64_t my_elems = dp->plan.chunk_elems[lr];
-      stats_.raw_bytes += ((dp->plan.numel - my_elems) + my_elems * (uint64_t)(lw - 1)) * (uint64_t)elsize;
+      launch_fused(Launch{dp, false, sub++}, data, prescale, rng, stream);
     }
     return;
   }

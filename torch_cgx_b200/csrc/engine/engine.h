@@ -101,6 +101,26 @@ class AllreduceEngine {
   void intra_stage(bool cuda, void* data, int dtype, const std::vector<LayerSpec>& group, bool skip_incomplete,
                    float prescale, RngParams rng, cudaStream_t stream);
 
+  // Fast path for registered DDP buckets: once a bucket's plans are known (and nothing that
+  // influences them changed) a call is just "launch these kernels" -- no layer extraction,
+  // no fusion split, no plan hashing on the host.
+  struct Launch {
+    const DevicePlan* dp;
+    bool oneshot;
+    uint32_t rng_sub;  // low bits of the RNG sequence used for this launch
+  };
+  struct BucketFast {
+    uint64_t registry_version = 0;
+    int64_t numel = -1;
+    int dtype = -1;
+    int env_bits = 0, env_bucket = 0;
+    bool skip_incomplete = false;
+    std::vector<Launch> launches;
+  };
+  std::vector<BucketFast> fast_;
+  std::vector<Launch>* recording_ = nullptr;
+  void launch_fused(const Launch& l, void* data, float prescale, RngParams rng, cudaStream_t stream);
+
   int rank_, world_;
   int local_size_;
   EngineConfig cfg_;

@@ -1,1 +1,1 @@
-from .hooks import CGXState, cgx_hook  # noqa: F401
+from .hooks import CGXState, cgx_hook, register_cgx_hook  # noqa: F401

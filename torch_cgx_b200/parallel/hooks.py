@@ -75,8 +75,17 @@ class CGXState(object):
         self.step = 0
 
 
+_NATIVE_CACHE = {}
+
+
 def _native_backend(group, tensor: torch.Tensor):
-    return _backend.get_backend(group, tensor.device)
+    # resolved once per (group, device type): the lookup costs several microseconds per bucket
+    key = (id(group), tensor.device.type)
+    hit = _NATIVE_CACHE.get(key)
+    if hit is None or hit[0] is not group:
+        hit = (group, _backend.get_backend(group, tensor.device))
+        _NATIVE_CACHE[key] = hit
+    return hit[1]
 
 
 def _allreduce_fut(process_group, tensor: torch.Tensor, bucket_idx: int = -1) -> torch.futures.Future[torch.Tensor]:
@@ -107,3 +116,29 @@ def cgx_hook(state: CGXState, bucket: dist.GradBucket) -> torch.futures.Future[t
         state.step += 1
         state.layer_idx = 0
     return _allreduce_fut(state.process_group, bucket.buffer(), bucket.index() if registered else -1)
+
+
+def register_cgx_hook(ddp_model, state: CGXState):
+    """Install the compressed-allreduce hook on a DistributedDataParallel model.
+
+    With the ``cgx`` backend this registers the **native C++ hook** directly on DDP's reducer
+    (no Python in the per-bucket path); with any other backend it falls back to
+    ``ddp_model.register_comm_hook(state, cgx_hook)``. Returns the native state handle or None.
+    """
+    from .. import _C
+
+    params = [p for p in ddp_model.parameters() if p.requires_grad]
+    device = params[0].device if params else torch.device("cpu")
+    native = _backend.get_backend(state.process_group, device)
+    if native is None:
+        ddp_model.register_comm_hook(state, cgx_hook)
+        return None
+    handle = _C.register_native_hook(ddp_model.reducer, native, int(state.layer_min_size),
+                                     int(state.quantization_bits), int(state.quantization_bucket_size),
+                                     int(state.register_step))
+    try:
+        ddp_model.logger._set_comm_hook_name("cgx_native_hook")
+    except Exception:  # noqa: BLE001
+        pass
+    state.native = handle
+    return handle
