@@ -143,3 +143,9 @@ def _ddp_cpu_native_hook(rank, world):
 
 def test_native_cpp_hook_matches_python_hook():
     spawn(_ddp_cpu_native_hook, 2)
+
+
+def test_ddp_hook_cpu_compressed_async_worker():
+    # CPU tensors through the compressed generic reducers on the backend's host worker thread
+    # (futures complete asynchronously; replicas must still end bit-identical)
+    spawn(_ddp_cpu, 2, env={"CGX_COMPRESS_CPU": "1"})

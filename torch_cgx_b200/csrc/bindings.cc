@@ -371,6 +371,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     d["intra_broadcast"] = c.intra_broadcast;
     d["intra_compress"] = c.intra_compress;
     d["dummy_compression"] = c.dummy_compression;
+    d["remote_buf"] = c.remote_buf;
+    d["oneshot_max_bytes"] = c.oneshot_max_bytes;
     d["lanes"] = c.lanes;
     d["timeout_ms"] = c.timeout_ms;
     d["local_size"] = c.local_size;

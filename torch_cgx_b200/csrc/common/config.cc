@@ -105,6 +105,7 @@ EngineConfig EngineConfig::read() {
   c.intra_broadcast = env_bool(kEnvIntraBroadcast, true);
   c.intra_compress = env_bool(kEnvIntraCompress, true);
   c.dummy_compression = env_bool(kEnvDummyCompression, false);
+  c.remote_buf = env_bool(kEnvRemoteBuf, true);
   c.lanes = (int)env_int(kEnvLanes, 0);
   c.timeout_ms = std::max<int64_t>(1, env_int(kEnvTimeoutMs, 30000));
   c.local_size = (int)env_int(kEnvLocalSize, 0);

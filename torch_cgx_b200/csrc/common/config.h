@@ -82,6 +82,9 @@ struct EngineConfig {
   bool intra_broadcast = true;
   bool intra_compress = true;
   bool dummy_compression = false;
+  bool remote_buf = true;  // CGX_REMOTE_BUF_COMPRESSION: quantize straight into peer-visible memory. The fused
+                           // kernel always does (with proper signalling, unlike the reference's experimental
+                           // variant); the variable is accepted for compatibility.
   int lanes = 0;
   int64_t timeout_ms = 30000;
   int local_size = 0;

@@ -194,7 +194,10 @@ void AllreduceEngine::intra_stage(bool cuda, void* data, int dtype, const std::v
                                   bool skip_incomplete, float prescale, RngParams rng, cudaStream_t stream) {
   GenericPath& g = cuda ? gen_cuda_ : gen_cpu_;
   const int elsize = dtype_size(dtype);
-  if (cuda && fused_ && cfg_.inner_comm == CommType::kP2P) {
+  // the fused kernel implements SRA (+ the one-shot variant); an explicitly requested Ring or
+  // all-to-all intra-node reduction goes through the generic reducers instead
+  const bool want_fused = cfg_.inner_reduction == ReductionType::kSRA || !g.intra;
+  if (cuda && fused_ && cfg_.inner_comm == CommType::kP2P && want_fused) {
     // latency-bound messages: single-hop one-shot kernel
     if (fused_->world() > 1 && cfg_.oneshot_max_bytes > 0) {
       uint64_t n = 0;

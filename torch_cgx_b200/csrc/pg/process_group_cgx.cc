@@ -69,6 +69,51 @@ bool WorkCGX::wait(std::chrono::milliseconds /*timeout*/) {
 std::vector<at::Tensor> WorkCGX::result() { return outputs_; }
 c10::intrusive_ptr<c10::ivalue::Future> WorkCGX::getFuture() { return future_; }
 
+// ------------------------------------------------------------- HostWorker ---
+HostWorker::HostWorker() : th_([this] { loop(); }) {}
+
+HostWorker::~HostWorker() {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  if (th_.joinable()) th_.join();
+}
+
+void HostWorker::submit(std::function<void()> job) {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    q_.push_back(std::move(job));
+  }
+  cv_.notify_one();
+}
+
+void HostWorker::drain() {
+  std::unique_lock<std::mutex> g(mu_);
+  idle_cv_.wait(g, [this] { return q_.empty() && !busy_; });
+}
+
+void HostWorker::loop() {
+  for (;;) {
+    std::function<void()> job;
+    {
+      std::unique_lock<std::mutex> g(mu_);
+      cv_.wait(g, [this] { return stop_ || !q_.empty(); });
+      if (q_.empty()) return;  // stop requested and nothing left
+      job = std::move(q_.front());
+      q_.pop_front();
+      busy_ = true;
+    }
+    job();  // jobs report their own errors through their futures
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      busy_ = false;
+    }
+    idle_cv_.notify_all();
+  }
+}
+
 // -------------------------------------------------------- ProcessGroupCGX ---
 ProcessGroupCGX::ProcessGroupCGX(const c10::intrusive_ptr<c10d::Store>& store, int rank, int size,
                                  std::chrono::milliseconds timeout,
@@ -104,6 +149,7 @@ ProcessGroupCGX::ProcessGroupCGX(const c10::intrusive_ptr<c10d::Store>& store, i
 }
 
 ProcessGroupCGX::~ProcessGroupCGX() {
+  worker_.reset();  // finishes queued host jobs before the engine goes away
   if (engine_ && device_ >= 0) {
     c10::cuda::CUDAGuard g(device_);
     cudaDeviceSynchronize();
@@ -215,15 +261,25 @@ c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::engine_allreduce(at::Tensor& t, 
 }
 
 c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::engine_allreduce_cpu(at::Tensor& t, bool average, int bucket_idx) {
-  // host tensors: synchronous in the caller's thread (the reference queues them to its worker
-  // thread, ProcessGroupCGX.cc:300-339; Gloo send/recv already overlap internally)
+  // host tensors: queued to the worker thread in call order (reference: enqueue/runLoop,
+  // ProcessGroupCGX.cc:300-339); the returned Work's future completes when the job is done, errors
+  // are delivered through it
   {
     std::lock_guard<std::mutex> lk(mu_);
     ++seq_;
-    engine_->allreduce_cpu(t.data_ptr(), to_cgx_dtype(t.scalar_type()), t.numel(), average, bucket_idx);
+    if (!worker_) worker_ = std::make_unique<HostWorker>();
   }
   auto fut = c10::make_intrusive<c10::ivalue::Future>(c10::ListType::create(c10::TensorType::get()));
-  fut->markCompleted(at::IValue(std::vector<at::Tensor>{t}));
+  at::Tensor tensor = t;
+  const int dtype = to_cgx_dtype(t.scalar_type());
+  worker_->submit([this, fut, tensor, dtype, average, bucket_idx]() mutable {
+    try {
+      engine_->allreduce_cpu(tensor.data_ptr(), dtype, tensor.numel(), average, bucket_idx);
+      fut->markCompleted(at::IValue(std::vector<at::Tensor>{tensor}));
+    } catch (...) {
+      fut->setError(std::current_exception());
+    }
+  });
   return c10d::Work::create_from_future(fut);
 }
 
@@ -366,7 +422,8 @@ c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::recvAnysource(std::vector<at::Te
 }
 
 c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::barrier(const c10d::BarrierOptions& opts) {
-  // A barrier must also drain this backend's own side stream.
+  // A barrier must also drain this backend's own host worker and side stream.
+  if (worker_) worker_->drain();
   if (cuda_ready_ && device_ >= 0) {
     c10::cuda::CUDAGuard g(device_);
     comm_stream_->synchronize();

@@ -25,8 +25,12 @@
 #include <torch/csrc/distributed/c10d/Work.hpp>
 
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <optional>
 #include <string>
 #include <vector>
@@ -61,6 +65,28 @@ class WorkCGX : public c10d::Work {
 struct CgxTopology {
   int local_size = 0;  // 0 = whole group is one node
   c10::intrusive_ptr<c10d::Backend> cpu_local, cpu_cross, cuda_local, cuda_cross;
+};
+
+// Host-side worker: a single thread draining a FIFO of jobs, the role of
+// ProcessGroupCGX::runLoop / enqueue in the reference (/root/reference/src/
+// ProcessGroupCGX.cc:300-339). Only the *host-tensor* compressed allreduce uses it
+// (blocking Gloo send/recv must not stall the autograd thread); the CUDA path
+// needs no thread because it is a single stream-ordered kernel launch.
+class HostWorker {
+ public:
+  HostWorker();
+  ~HostWorker();
+  void submit(std::function<void()> job);
+  void drain();  // block until every submitted job has finished
+
+ private:
+  void loop();
+  std::mutex mu_;
+  std::condition_variable cv_, idle_cv_;
+  std::deque<std::function<void()>> q_;
+  bool stop_ = false;
+  bool busy_ = false;
+  std::thread th_;
 };
 
 class ProcessGroupCGX : public c10d::Backend {
@@ -160,6 +186,7 @@ class ProcessGroupCGX : public c10d::Backend {
   c10::DeviceIndex device_ = -1;
   std::mutex mu_;
   uint64_t seq_ = 0;
+  std::unique_ptr<HostWorker> worker_;  // created on first use
 };
 
 }  // namespace cgx
