@@ -107,7 +107,7 @@ EngineConfig EngineConfig::read() {
   c.dummy_compression = env_bool(kEnvDummyCompression, false);
   c.remote_buf = env_bool(kEnvRemoteBuf, true);
   c.lanes = (int)env_int(kEnvLanes, 0);
-  c.timeout_ms = std::max<int64_t>(1, env_int(kEnvTimeoutMs, 30000));
+  c.timeout_ms = std::max<int64_t>(1, env_int(kEnvTimeoutMs, 120000));
   c.local_size = (int)env_int(kEnvLocalSize, 0);
   c.min_lane_elems = (uint32_t)std::max<int64_t>(8, env_int(kEnvMinLaneElems, 2048));
   c.oneshot_max_bytes = std::max<int64_t>(0, env_int(kEnvOneshotMaxBytes, 2 << 20));

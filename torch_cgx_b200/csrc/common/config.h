@@ -86,7 +86,7 @@ struct EngineConfig {
                            // kernel always does (with proper signalling, unlike the reference's experimental
                            // variant); the variable is accepted for compatibility.
   int lanes = 0;
-  int64_t timeout_ms = 30000;
+  int64_t timeout_ms = 120000;
   int local_size = 0;
   uint32_t min_lane_elems = 2048;
   int64_t oneshot_max_bytes = 2 << 20;

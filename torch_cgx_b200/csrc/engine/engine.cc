@@ -133,7 +133,7 @@ void AllreduceEngine::allreduce_cuda(void* data, int dtype, int64_t numel, bool 
     if ((size_t)explicit_bucket >= fast_.size()) fast_.resize((size_t)explicit_bucket + 1);
     BucketFast& f = fast_[(size_t)explicit_bucket];
     const uint64_t ver = LayerRegistry::instance().version();
-    if (f.registry_version == ver && f.numel == numel && f.dtype == dtype && f.env_bits == env.bits &&
+    if (f.registry_version == ver && f.plan_generation == fused_->generation() && f.numel == numel && f.dtype == dtype && f.env_bits == env.bits &&
         f.env_bucket == env.bucket_size && f.skip_incomplete == env.skip_incomplete && !f.launches.empty()) {
       fused_->check_status();
       ++call_seq_;
@@ -162,6 +162,7 @@ void AllreduceEngine::allreduce_cuda(void* data, int dtype, int64_t numel, bool 
     }
     recording_ = nullptr;
     f.registry_version = ver;
+    f.plan_generation = fused_->generation();
     f.numel = numel;
     f.dtype = dtype;
     f.env_bits = env.bits;

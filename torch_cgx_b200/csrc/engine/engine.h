@@ -111,6 +111,7 @@ class AllreduceEngine {
   };
   struct BucketFast {
     uint64_t registry_version = 0;
+    uint64_t plan_generation = 0;
     int64_t numel = -1;
     int dtype = -1;
     int env_bits = 0, env_bucket = 0;

@@ -66,6 +66,17 @@ const DevicePlan* FusedSra::prepare_impl(const std::vector<LayerSpec>& layers, i
   const uint64_t key = plan_key(layers, opt);
   auto it = cache_.find(key);
   if (it == cache_.end()) {
+    if (cache_.size() >= kMaxCachedPlans) {
+      // workloads with ever-changing message sizes: drop everything (kernels that still read the
+      // old tables are ordered before the frees by the synchronize) and invalidate derived caches
+      cuda_check(cudaStreamSynchronize(stream), "sync before trimming the plan cache");
+      for (auto& kv : cache_) {
+        if (kv.second->d_blocks) cudaFree(kv.second->d_blocks);
+        if (kv.second->d_lane_first) cudaFree(kv.second->d_lane_first);
+      }
+      cache_.clear();
+      ++generation_;
+    }
     auto dp = std::make_unique<DevicePlan>();
     dp->plan = build_plan(layers, opt);
     int ub = -1;

@@ -59,6 +59,8 @@ class FusedSra {
   std::vector<uint64_t> read_trace();
   int last_lanes() const { return last_lanes_; }
   uint64_t launches() const { return launches_; }
+  // bumped whenever cached DevicePlan pointers become invalid (cache trimmed)
+  uint64_t generation() const { return generation_; }
   uint32_t epoch() const { return epoch_; }
 
  private:
@@ -73,6 +75,8 @@ class FusedSra {
   bool trace_on_ = false;
   int last_lanes_ = 0;
   uint32_t oneshot_calls_ = 0;
+  uint64_t generation_ = 1;
+  static constexpr size_t kMaxCachedPlans = 1024;
   const DevicePlan* prepare_impl(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
                                  cudaStream_t stream, int plan_world, uint32_t capacity);
   void launch(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream,
