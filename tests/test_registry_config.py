@@ -134,3 +134,17 @@ def test_bench_reference_arm_reports_unavailable():
     assert out.returncode == 0
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and "unavailable" in d
+
+
+def test_compression_context_manager(clean_cgx_env, monkeypatch):
+    monkeypatch.setenv("CGX_COMPRESSION_BUCKET_SIZE", "128")
+    assert C.engine_config()["bits"] == 32
+    with cgx.compression(bits=2, bucket_size=256, stochastic=True, seed=9):
+        cfg = C.engine_config()
+        assert (cfg["bits"], cfg["bucket_size"], cfg["stochastic"], cfg["seed"]) == (2, 256, True, 9)
+        with cgx.compression(bits=8):
+            assert C.engine_config()["bits"] == 8 and C.engine_config()["bucket_size"] == 256
+        assert C.engine_config()["bits"] == 2
+    cfg = C.engine_config()
+    assert cfg["bits"] == 32 and cfg["bucket_size"] == 128 and cfg["stochastic"] is False
+    assert "CGX_SEED" not in os.environ

@@ -27,6 +27,7 @@ from .backend import (  # noqa: E402
     set_quantization_bits,
     set_quantization_bucket_size,
 )
+from .parallel.functional import all_reduce, compression  # noqa: E402
 from .parallel.hooks import CGXState, cgx_hook, register_cgx_hook  # noqa: E402
 from .utils.launch import map_launcher_env  # noqa: E402
 from . import models, ops, utils  # noqa: E402,F401
@@ -36,7 +37,9 @@ register_backend()
 __all__ = [
     "BACKEND_NAME",
     "CGXState",
+    "all_reduce",
     "cgx_hook",
+    "compression",
     "get_backend",
     "map_launcher_env",
     "register_backend",
