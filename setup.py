@@ -20,6 +20,7 @@ SOURCES = [
     "common/config.cc",
     "common/layers.cc",
     "common/sra_sim.cc",
+    "comm/fd_channel.cc",
     "comm/symmetric_heap.cc",
     "reduce/fused_sra.cc",
     "reduce/block_backend.cc",
@@ -27,8 +28,11 @@ SOURCES = [
     "pg/c10d_communicator.cc",
     "pg/comm_hook.cc",
     "engine/engine.cc",
-    "kernels/sra_fused.cu",
-    "kernels/quantize.cu",
+    "kernels/sra_f32.cu",
+    "kernels/sra_f16.cu",
+    "kernels/sra_bf16.cu",
+    "kernels/sra_dispatch.cu",
+    "kernels/item_kernels.cu",
     "pg/process_group_cgx.cc",
     "bindings.cc",
 ]

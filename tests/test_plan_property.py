@@ -53,9 +53,36 @@ def test_plan_invariants(specs, world, lanes, skip_incomplete, dtype):
             if bits >= 32:
                 cur += (n * es + 15) // 16 * 16
             else:
-                cur += (-(-n // bucket) * 8 + 15) // 16 * 16 + (-(-n // 8) * bits + 15) // 16 * 16
+                # every bucket starts a fresh pack group
+                groups = (n // bucket) * -(-bucket // 8) + -(-(n % bucket) // 8)
+                cur += (-(-n // bucket) * 8 + 15) // 16 * 16 + (groups * bits + 15) // 16 * 16
         assert cur == plan["chunk_wire_bytes"][c] <= plan["max_chunk_wire"]
     assert sum(plan["chunk_elems"]) == total
+    # warp items: tile every block exactly once, in order, with consistent wire offsets
+    items = [tuple(int(v) for v in row) for row in plan["items"]]
+    bif, itf, slice_elems = plan["block_item_first"], plan["item_first"], plan["slice_elems"]
+    assert len(bif) == len(blocks) + 1 and bif[-1] == len(items) and itf[-1] == len(items)
+    assert slice_elems in (512, 1024)
+    for k in range(world * G):
+        assert itf[k] == bif[lf[k]]
+    for b, (off, n, bits, bucket, woff) in enumerate(blocks):
+        pos = off
+        mb = (-(-n // bucket) * 8 + 15) // 16 * 16
+        gpb = -(-bucket // 8)
+        for eo, mo, po, kind, lg, ibits, cnt in items[bif[b]:bif[b + 1]]:
+            assert eo == pos and cnt > 0 and ibits == (32 if bits >= 32 else bits)
+            rel = eo - off
+            if bits >= 32:
+                assert kind in (2, 3) and (kind == 2) == (cnt == 512) and mo == po == woff + rel * es
+            else:
+                assert rel % bucket == 0 and mo == woff + (rel // bucket) * 8
+                assert po == woff + mb + (rel // bucket) * gpb * bits
+                if kind == 0:
+                    assert cnt == slice_elems and bucket == 8 << lg and bucket <= slice_elems
+                else:
+                    assert kind == 1 and cnt <= bucket
+            pos += cnt
+        assert pos == off + n
 
 
 @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])

@@ -82,6 +82,22 @@ py::dict plan_to_dict(const Plan& p) {
     bp[i * 5 + 4] = p.blocks[i].wire_off;
   }
   d["blocks"] = blocks;
+  auto items = at::empty({(int64_t)p.items.size(), 7}, at::kLong);
+  auto* ip = items.data_ptr<int64_t>();
+  for (size_t i = 0; i < p.items.size(); ++i) {
+    ip[i * 7 + 0] = p.items[i].elem_off;
+    ip[i * 7 + 1] = p.items[i].meta_off;
+    ip[i * 7 + 2] = p.items[i].pay_off;
+    ip[i * 7 + 3] = item_kind(p.items[i]);
+    ip[i * 7 + 4] = item_lpb_log2(p.items[i]);
+    ip[i * 7 + 5] = item_bits(p.items[i]);
+    ip[i * 7 + 6] = item_n(p.items[i]);
+  }
+  d["items"] = items;  // rows: elem_off, meta_off, pay_off, kind, log2(bucket/8), bits, n
+  d["item_first"] = std::vector<int64_t>(p.item_first.begin(), p.item_first.end());
+  d["block_item_first"] = std::vector<int64_t>(p.block_item_first.begin(), p.block_item_first.end());
+  d["slice_elems"] = p.slice_elems;
+  d["uniform_bits"] = p.uniform_bits;
   d["lane_first"] = std::vector<int64_t>(p.lane_first.begin(), p.lane_first.end());
   d["chunk_wire_bytes"] = std::vector<int64_t>(p.chunk_wire_bytes.begin(), p.chunk_wire_bytes.end());
   d["chunk_elems"] = std::vector<int64_t>(p.chunk_elems.begin(), p.chunk_elems.end());
@@ -152,15 +168,21 @@ at::Tensor py_quantize(const at::Tensor& t, const std::vector<LayerTuple>& layer
   c10::cuda::CUDAGuard g(t.device());
   auto stream = c10::cuda::getCurrentCUDAStream();
   at::Tensor wire = at::zeros({(int64_t)world, (int64_t)row}, t.options().dtype(at::kByte));
-  at::Tensor dblocks = at::empty({(int64_t)(plan.blocks.size() * sizeof(BlockDesc))}, t.options().dtype(at::kByte));
-  cuda_check(cudaMemcpyAsync(dblocks.data_ptr(), plan.blocks.data(), plan.blocks.size() * sizeof(BlockDesc),
+  at::Tensor ditems = at::empty({(int64_t)(plan.items.size() * sizeof(WarpItem) + 16)}, t.options().dtype(at::kByte));
+  cuda_check(cudaMemcpyAsync(ditems.data_ptr(), plan.items.data(), plan.items.size() * sizeof(WarpItem),
                              cudaMemcpyHostToDevice, stream),
-             "upload blocks");
-  for (int c = 0; c < world; ++c)
-    cuda_check(launch_quantize_blocks(t.data_ptr(), dt, (const BlockDesc*)dblocks.data_ptr(), plan.chunk_begin(c),
-                                      plan.chunk_end(c) - plan.chunk_begin(c),
-                                      wire.data_ptr<uint8_t>() + (size_t)c * row, prescale, key, stream),
-               "quantize_blocks");
+             "upload items");
+  for (int c = 0; c < world; ++c) {
+    ItemKernelArgs a;
+    a.items = (const WarpItem*)ditems.data_ptr();
+    a.first = plan.item_first[(size_t)c * plan.lanes];
+    a.count = plan.item_first[(size_t)(c + 1) * plan.lanes] - a.first;
+    a.dtype = dt;
+    a.slice_elems = (int)plan.slice_elems;
+    a.uniform_bits = plan.uniform_bits;
+    cuda_check(launch_quantize_items(a, t.data_ptr(), wire.data_ptr<uint8_t>() + (size_t)c * row, prescale, key, stream),
+               "quantize_items");
+  }
   return wire;
 }
 
@@ -183,15 +205,21 @@ at::Tensor py_dequantize(const at::Tensor& wire, const at::Tensor& like, const s
   }
   c10::cuda::CUDAGuard g(like.device());
   auto stream = c10::cuda::getCurrentCUDAStream();
-  at::Tensor dblocks = at::empty({(int64_t)(plan.blocks.size() * sizeof(BlockDesc))}, like.options().dtype(at::kByte));
-  cuda_check(cudaMemcpyAsync(dblocks.data_ptr(), plan.blocks.data(), plan.blocks.size() * sizeof(BlockDesc),
+  at::Tensor ditems = at::empty({(int64_t)(plan.items.size() * sizeof(WarpItem) + 16)}, like.options().dtype(at::kByte));
+  cuda_check(cudaMemcpyAsync(ditems.data_ptr(), plan.items.data(), plan.items.size() * sizeof(WarpItem),
                              cudaMemcpyHostToDevice, stream),
-             "upload blocks");
-  for (int c = 0; c < world; ++c)
-    cuda_check(launch_dequantize_blocks(wire.data_ptr<uint8_t>() + (size_t)c * row, dt,
-                                        (const BlockDesc*)dblocks.data_ptr(), plan.chunk_begin(c),
-                                        plan.chunk_end(c) - plan.chunk_begin(c), out.data_ptr(), stream),
-               "dequantize_blocks");
+             "upload items");
+  for (int c = 0; c < world; ++c) {
+    ItemKernelArgs a;
+    a.items = (const WarpItem*)ditems.data_ptr();
+    a.first = plan.item_first[(size_t)c * plan.lanes];
+    a.count = plan.item_first[(size_t)(c + 1) * plan.lanes] - a.first;
+    a.dtype = dt;
+    a.slice_elems = (int)plan.slice_elems;
+    a.uniform_bits = plan.uniform_bits;
+    cuda_check(launch_dequantize_items(a, wire.data_ptr<uint8_t>() + (size_t)c * row, out.data_ptr(), stream),
+               "dequantize_items");
+  }
   return out;
 }
 

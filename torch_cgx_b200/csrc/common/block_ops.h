@@ -106,9 +106,10 @@ inline void load_block(const void* src, int dtype, const BlockDesc& d, float pre
   for (uint32_t i = 0; i < n; ++i) acc[i] = load_elem(src, dtype, (uint64_t)d.elem_off + i) * prescale;
 }
 
-// Quantize n fp32 values into the block's wire record.
+// Quantize n fp32 values into the block's wire record. Buckets are self-contained: bucket k
+// owns meta[k] and the pack groups [k * bucket_groups(B), ...) of the payload.
 inline void quantize_block(const float* acc, int dtype, const BlockDesc& d, uint8_t* rec,
-                           const RngKey& rng, uint32_t block_id) {
+                           const RngKey& rng, uint32_t /*block_id*/) {
   const uint32_t n = block_n(d);
   const int bits = block_bits(d);
   if (bits >= kRawBits) {
@@ -119,43 +120,37 @@ inline void quantize_block(const float* acc, int dtype, const BlockDesc& d, uint
   }
   const uint32_t B = d.bucket;
   const uint32_t nb = block_num_buckets(n, B);
+  const uint32_t gpb = bucket_groups(B);
   BucketMeta* meta = reinterpret_cast<BucketMeta*>(rec);
-  std::vector<float> inv(nb);
+  uint8_t* pay = rec + block_meta_bytes(n, B);
+  const float maxlvl = (float)max_level(bits);
   for (uint32_t b = 0; b < nb; ++b) {
-    uint32_t lo = b * B, hi = lo + B < n ? lo + B : n;
+    const uint32_t lo = b * B, hi = lo + B < n ? lo + B : n;
     float mn = acc[lo], mx = acc[lo];
     for (uint32_t i = lo + 1; i < hi; ++i) {
       mn = nan_min(mn, acc[i]);
       mx = nan_max(mx, acc[i]);
     }
     meta[b] = make_meta(mn, mx, bits);
-    inv[b] = inv_unit(meta[b].unit);
+    const float inv = inv_unit(meta[b].unit);
+    const uint32_t groups = div_up(hi - lo, 8u);
+    for (uint32_t g = 0; g < groups; ++g) {
+      const uint32_t i0 = lo + g * 8u;
+      float r[8];
+      rounding_offsets8(rng, d.elem_off + i0, r);
+      uint32_t q[8];
+      for (int j = 0; j < 8; ++j) q[j] = (i0 + j < hi) ? encode_level(acc[i0 + j], meta[b].min, inv, r[j], maxlvl) : 0u;
+      const uint64_t w = pack8(q, bits);
+      uint8_t* dst = pay + (size_t)(b * gpb + g) * bits;
+      for (int t = 0; t < bits; ++t) dst[t] = (uint8_t)(w >> (8 * t));
+    }
   }
   {
     uint32_t used = nb * 8u, tot = block_meta_bytes(n, B);
     std::memset(rec + used, 0, tot - used);
   }
-  uint8_t* pay = rec + block_meta_bytes(n, B);
-  const float maxlvl = (float)max_level(bits);
-  const uint32_t groups = div_up(n, 8u);
-  for (uint32_t g = 0; g < groups; ++g) {
-    float r[8];
-    rounding_offsets8(rng, block_id, g, r);
-    uint32_t q[8];
-    for (int j = 0; j < 8; ++j) {
-      uint32_t i = g * 8u + (uint32_t)j;
-      if (i < n) {
-        uint32_t b = i / B;
-        q[j] = encode_level(acc[i], meta[b].min, inv[b], r[j], maxlvl);
-      } else {
-        q[j] = 0;
-      }
-    }
-    uint64_t w = pack8(q, bits);
-    for (int t = 0; t < bits; ++t) pay[(size_t)g * bits + t] = (uint8_t)(w >> (8 * t));
-  }
   {
-    uint32_t used = groups * (uint32_t)bits, tot = block_payload_bytes(n, bits);
+    uint32_t used = block_num_groups(n, B) * (uint32_t)bits, tot = block_payload_bytes(n, bits, B);
     std::memset(pay + used, 0, tot - used);
   }
 }
@@ -171,17 +166,23 @@ inline void decode_block_foreach(const uint8_t* rec, int dtype, const BlockDesc&
     return;
   }
   const uint32_t B = d.bucket;
+  const uint32_t nb = block_num_buckets(n, B);
+  const uint32_t gpb = bucket_groups(B);
   const BucketMeta* meta = reinterpret_cast<const BucketMeta*>(rec);
   const uint8_t* pay = rec + block_meta_bytes(n, B);
-  const uint32_t groups = div_up(n, 8u);
-  for (uint32_t g = 0; g < groups; ++g) {
-    uint64_t w = 0;
-    for (int t = 0; t < bits; ++t) w |= (uint64_t)pay[(size_t)g * bits + t] << (8 * t);
-    for (int j = 0; j < 8; ++j) {
-      uint32_t i = g * 8u + (uint32_t)j;
-      if (i >= n) break;
-      const BucketMeta& m = meta[i / B];
-      f(i, decode_level(unpack1(w, j, bits), m.unit, m.min));
+  for (uint32_t b = 0; b < nb; ++b) {
+    const uint32_t lo = b * B, hi = lo + B < n ? lo + B : n;
+    const BucketMeta m = meta[b];
+    const uint32_t groups = div_up(hi - lo, 8u);
+    for (uint32_t g = 0; g < groups; ++g) {
+      const uint8_t* src = pay + (size_t)(b * gpb + g) * bits;
+      uint64_t w = 0;
+      for (int t = 0; t < bits; ++t) w |= (uint64_t)src[t] << (8 * t);
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t i = lo + g * 8u + (uint32_t)j;
+        if (i >= hi) break;
+        f(i, decode_level(unpack1(w, j, bits), m.unit, m.min));
+      }
     }
   }
 }

@@ -109,7 +109,8 @@ EngineConfig EngineConfig::read() {
   c.lanes = (int)env_int(kEnvLanes, 0);
   c.timeout_ms = std::max<int64_t>(1, env_int(kEnvTimeoutMs, 120000));
   c.local_size = (int)env_int(kEnvLocalSize, 0);
-  c.min_lane_elems = (uint32_t)std::max<int64_t>(8, env_int(kEnvMinLaneElems, 2048));
+  c.min_lane_elems = (uint32_t)std::max<int64_t>(8, env_int(kEnvMinLaneElems, 4096));
+  c.overlap_lanes = (int)std::max<int64_t>(0, env_int(kEnvOverlapLanes, 64));
   c.oneshot_max_bytes = std::max<int64_t>(0, env_int(kEnvOneshotMaxBytes, 2 << 20));
   return c;
 }

@@ -39,6 +39,10 @@ constexpr const char* kEnvLocalSize = "CGX_LOCAL_SIZE";             // ranks per
 constexpr const char* kEnvLogLevel = "CGX_LOG_LEVEL";               // 0 silent, 1 info, 2 debug
 constexpr const char* kEnvMinLaneElems = "CGX_MIN_LANE_ELEMS";
 constexpr const char* kEnvOneshotMaxBytes = "CGX_ONESHOT_MAX_BYTES";  // messages up to this size take the one-shot kernel (0 = never)
+constexpr const char* kEnvOverlapLanes = "CGX_OVERLAP_LANES";  // CTAs of a DDP-bucket allreduce that overlaps with backward (0 = no cap)
+constexpr const char* kEnvVmm = "CGX_VMM";                      // 0: cudaMalloc + cudaIpc heap instead of VMM + fd handles
+constexpr const char* kEnvNvls = "CGX_NVLS";                    // 0: never create the NVLS multicast mapping
+constexpr const char* kEnvNvlsReduce = "CGX_NVLS_REDUCE";       // 0: raw layers use the two-shot path even with NVLS
 
 constexpr int kDefaultBits = 32;          // 32 == compression off
 constexpr int kDefaultBucketSize = 512;   // reference compressor.h:32
@@ -88,8 +92,9 @@ struct EngineConfig {
   int lanes = 0;
   int64_t timeout_ms = 120000;
   int local_size = 0;
-  uint32_t min_lane_elems = 2048;
+  uint32_t min_lane_elems = 4096;
   int64_t oneshot_max_bytes = 2 << 20;
+  int overlap_lanes = 64;  // lanes of an allreduce issued from the DDP hook (backward still needs the SMs)
   static EngineConfig read();
 };
 

@@ -46,12 +46,12 @@ CGX_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
   return r;
 }
 
-// uniform in [0,1) with 24 bits of resolution (exactly representable in fp32)
-CGX_HD float u32_to_unit_float(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+// uniform in [0,1) with 16 bits of resolution (exactly representable in fp32)
+CGX_HD float u16_to_unit_float(uint32_t x) { return (float)(x & 0xFFFFu) * (1.0f / 65536.0f); }
 
 // Parameters that select a random stream: (seed, call sequence number, a
-// stream id mixing rank and SRA phase). The per-element counter is
-// (group index inside the block, half, block id).
+// stream id mixing rank and SRA phase). The per-group counter is the index of
+// the group's first element.
 struct RngKey {
   uint32_t seed_lo;
   uint32_t seed_hi;
@@ -60,20 +60,25 @@ struct RngKey {
   uint32_t enabled; // 0 => deterministic r = 0.5
 };
 
-// 8 rounding offsets for pack-group `group` of block `block_id`.
-CGX_HD void rounding_offsets8(const RngKey& k, uint32_t block_id, uint32_t group, float r[8]) {
+// Rounding offsets of one pack group (8 values): ONE Philox call keyed by the index (from the
+// tensor base) of the group's first element, 16 random bits per value: value j uses the low
+// (j even) or high (j odd) half of v[j/2]. Independent of how the buffer is cut into blocks,
+// chunks and lanes, so every code path (CPU, fused kernel, standalone kernels) agrees.
+CGX_HD Philox4 rounding_bits(const RngKey& k, uint32_t first_elem) {
+  return philox4x32_10(first_elem, 0u, 0u, k.seq, k.seed_lo ^ (k.stream * 0x9E3779B9u), k.seed_hi);
+}
+CGX_HD float rounding_from_bits(const Philox4& a, int j) {
+  return u16_to_unit_float(a.v[j >> 1] >> ((j & 1) * 16));
+}
+CGX_HD void rounding_offsets8(const RngKey& k, uint32_t first_elem, float r[8]) {
   if (!k.enabled) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = 0.5f;
     return;
   }
-  Philox4 a = philox4x32_10(group, 0u, block_id, k.seq, k.seed_lo ^ (k.stream * 0x9E3779B9u), k.seed_hi);
-  Philox4 b = philox4x32_10(group, 1u, block_id, k.seq, k.seed_lo ^ (k.stream * 0x9E3779B9u), k.seed_hi);
+  const Philox4 a = rounding_bits(k, first_elem);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    r[j] = u32_to_unit_float(a.v[j]);
-    r[4 + j] = u32_to_unit_float(b.v[j]);
-  }
+  for (int j = 0; j < 8; ++j) r[j] = rounding_from_bits(a, j);
 }
 
 }  // namespace cgx

@@ -35,6 +35,50 @@ void push_segment(std::vector<Segment>& segs, uint64_t off, uint64_t n, int bits
   segs.push_back(s);
 }
 
+// Flatten one block into warp items (wire.h). Full slices need whole power-of-two buckets and a
+// group-aligned start; everything else becomes one generic item per bucket.
+void emit_items(const BlockDesc& d, int elsize, uint32_t slice, std::vector<WarpItem>& out) {
+  const uint32_t n = block_n(d);
+  const int bits = block_bits(d);
+  if (bits >= kRawBits) {
+    for (uint32_t off = 0; off < n; off += kRawItemElems) {
+      const uint32_t cnt = std::min(kRawItemElems, n - off);
+      WarpItem it;
+      it.elem_off = d.elem_off + off;
+      it.meta_off = it.pay_off = d.wire_off + off * (uint32_t)elsize;
+      it.info = make_item_info(cnt == kRawItemElems ? kItemRaw : kItemRawTail, 0, kRawBits, cnt);
+      out.push_back(it);
+    }
+    return;
+  }
+  const uint32_t B = d.bucket;
+  const uint32_t mb = block_meta_bytes(n, B);
+  const uint32_t gpb = bucket_groups(B);
+  const bool pow2 = B >= 8 && (B & (B - 1)) == 0 && B <= slice;
+  uint32_t off = 0;
+  if (pow2) {
+    uint32_t lg = 0;
+    while ((8u << lg) < B) ++lg;
+    for (; off + slice <= n; off += slice) {
+      WarpItem it;
+      it.elem_off = d.elem_off + off;
+      it.meta_off = d.wire_off + (off / B) * 8u;
+      it.pay_off = d.wire_off + mb + (off / 8u) * (uint32_t)bits;
+      it.info = make_item_info(kItemFull, lg, bits, slice);
+      out.push_back(it);
+    }
+  }
+  for (; off < n; off += B) {  // off is a multiple of B: blocks start on bucket boundaries
+    const uint32_t cnt = std::min(B, n - off);
+    WarpItem it;
+    it.elem_off = d.elem_off + off;
+    it.meta_off = d.wire_off + (off / B) * 8u;
+    it.pay_off = d.wire_off + mb + (off / B) * gpb * (uint32_t)bits;
+    it.info = make_item_info(kItemBucket, 0, bits, cnt);
+    out.push_back(it);
+  }
+}
+
 }  // namespace
 
 Plan build_plan(const std::vector<LayerSpec>& layers, const PlanOptions& opt) {
@@ -72,6 +116,20 @@ Plan build_plan(const std::vector<LayerSpec>& layers, const PlanOptions& opt) {
   p.world = opt.world;
   p.dtype = opt.dtype;
   p.numel = total;
+  {
+    // 1024-element slices when every compressed layer quantizes in 1024-element buckets (the
+    // Python hook's default), else 512; common bit width of the compressed layers
+    bool any = false, all1024 = true;
+    int ub = -1;
+    for (const Segment& s : segs) {
+      if (s.bits >= kRawBits) continue;
+      any = true;
+      all1024 = all1024 && s.bucket == 1024;
+      ub = (ub == -1 || ub == s.bits) ? s.bits : 0;
+    }
+    p.slice_elems = (any && all1024) ? 1024u : 512u;
+    p.uniform_bits = ub > 0 ? ub : 0;
+  }
   uint64_t per_rank = total / (uint64_t)opt.world;
   uint64_t want = per_rank / std::max<uint32_t>(1u, opt.min_lane_elems);
   p.lanes = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)opt.lanes, want));
@@ -96,11 +154,13 @@ Plan build_plan(const std::vector<LayerSpec>& layers, const PlanOptions& opt) {
 
   const int elsize = dtype_size(opt.dtype);
   p.lane_first.assign(S + 1, 0);
+  p.item_first.assign(S + 1, 0);
   p.chunk_wire_bytes.assign(W, 0);
   p.chunk_elems.assign(W, 0);
   size_t seg = 0;
   for (uint64_t k = 0; k < S; ++k) {
     p.lane_first[k] = (uint32_t)p.blocks.size();
+    p.item_first[k] = (uint32_t)p.items.size();
     const int chunk = (int)(k / G);
     uint64_t a = cut[k], b = cut[k + 1];
     while (a < b) {
@@ -122,11 +182,15 @@ Plan build_plan(const std::vector<LayerSpec>& layers, const PlanOptions& opt) {
       if (woff + wb >= (1ull << 32)) throw std::invalid_argument("cgx plan: chunk wire size exceeds 4 GiB");
       p.chunk_wire_bytes[chunk] = (uint32_t)(woff + wb);
       p.chunk_elems[chunk] += n;
+      p.block_item_first.push_back((uint32_t)p.items.size());
+      emit_items(d, elsize, p.slice_elems, p.items);
       p.blocks.push_back(d);
       a = s.start + next;
     }
   }
   p.lane_first[S] = (uint32_t)p.blocks.size();
+  p.item_first[S] = (uint32_t)p.items.size();
+  p.block_item_first.push_back((uint32_t)p.items.size());
   for (int c = 0; c < W; ++c) {
     p.max_chunk_wire = std::max(p.max_chunk_wire, p.chunk_wire_bytes[c]);
     p.total_wire += p.chunk_wire_bytes[c];

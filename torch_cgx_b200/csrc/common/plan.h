@@ -44,6 +44,13 @@ struct Plan {
   std::vector<uint64_t> chunk_elems;      // [world]
   uint32_t max_chunk_wire = 0;
   uint64_t total_wire = 0;
+  // flattened warp work list (see wire.h), same (chunk, lane) slot order as `blocks`
+  std::vector<WarpItem> items;
+  std::vector<uint32_t> item_first;       // [world * lanes + 1]
+  std::vector<uint32_t> block_item_first; // [blocks + 1]: items of block b are [block_item_first[b], [b+1])
+  uint32_t slice_elems = 512;             // elements of a kItemFull item (512, or 1024 when every
+                                          // compressed layer uses 1024-element buckets)
+  int uniform_bits = 0;                   // bits shared by every compressed block, else 0
 
   uint32_t slot_begin(int chunk, int lane) const { return lane_first[(size_t)chunk * lanes + lane]; }
   uint32_t slot_end(int chunk, int lane) const { return lane_first[(size_t)chunk * lanes + lane + 1]; }

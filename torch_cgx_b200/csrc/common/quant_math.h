@@ -58,12 +58,28 @@ CGX_HD float nan_max(float a, float b) {
 
 CGX_HD uint32_t max_level(int bits) { return (1u << bits) - 1u; }
 
+// 1 / (2^bits - 1), correctly rounded to fp32 (a literal per width so that host and
+// device agree bit for bit and the device pays one FMUL instead of an IEEE division)
+CGX_HD float rcp_levels(int bits) {
+  switch (bits) {
+    case 1: return 1.0f;
+    case 2: return 1.0f / 3.0f;
+    case 3: return 1.0f / 7.0f;
+    case 4: return 1.0f / 15.0f;
+    case 5: return 1.0f / 31.0f;
+    case 6: return 1.0f / 63.0f;
+    case 7: return 1.0f / 127.0f;
+    default: return 1.0f / 255.0f;
+  }
+}
+
+// unit = (max - min) * fp32(1 / levels): one rounding for the difference, one for the product
 CGX_HD BucketMeta make_meta(float mn, float mx, int bits) {
   BucketMeta m;
 #if defined(__CUDA_ARCH__)
-  m.unit = __fdiv_rn(__fsub_rn(mx, mn), (float)max_level(bits));
+  m.unit = __fmul_rn(__fsub_rn(mx, mn), rcp_levels(bits));
 #else
-  m.unit = (mx - mn) / (float)max_level(bits);
+  m.unit = (mx - mn) * rcp_levels(bits);
 #endif
   m.min = mn;
   return m;

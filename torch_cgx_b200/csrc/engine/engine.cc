@@ -124,7 +124,7 @@ void AllreduceEngine::launch_fused(const Launch& l, void* data, float prescale, 
 }
 
 void AllreduceEngine::allreduce_cuda(void* data, int dtype, int64_t numel, bool average, int explicit_bucket,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, bool overlapped) {
   if (numel <= 0) return;
   CompressionEnv env = CompressionEnv::read();
   const bool cacheable = explicit_bucket >= 0 && explicit_bucket < 4096 && nodes() == 1 && fused_ &&
@@ -133,8 +133,9 @@ void AllreduceEngine::allreduce_cuda(void* data, int dtype, int64_t numel, bool 
     if ((size_t)explicit_bucket >= fast_.size()) fast_.resize((size_t)explicit_bucket + 1);
     BucketFast& f = fast_[(size_t)explicit_bucket];
     const uint64_t ver = LayerRegistry::instance().version();
-    if (f.registry_version == ver && f.plan_generation == fused_->generation() && f.numel == numel && f.dtype == dtype && f.env_bits == env.bits &&
-        f.env_bucket == env.bucket_size && f.skip_incomplete == env.skip_incomplete && !f.launches.empty()) {
+    if (f.registry_version == ver && f.plan_generation == fused_->generation() && f.numel == numel &&
+        f.dtype == dtype && f.env_bits == env.bits && f.env_bucket == env.bucket_size &&
+        f.skip_incomplete == env.skip_incomplete && f.overlapped == overlapped && !f.launches.empty()) {
       fused_->check_status();
       ++call_seq_;
       ++stats_.calls;
@@ -151,16 +152,23 @@ void AllreduceEngine::allreduce_cuda(void* data, int dtype, int64_t numel, bool 
       }
       return;
     }
-    // slow path once, recording what was launched
+    // slow path once, recording what was launched. A plan-cache trim in the middle of the call
+    // (generation bump) frees the plans recorded so far: keep the recording only if none happened.
     std::vector<Launch> rec;
     recording_ = &rec;
+    const uint64_t gen_before = fused_->generation();
     try {
-      allreduce_cuda_layers(data, dtype, resolve_layers(numel, cfg_, env, explicit_bucket), average, env, stream);
+      allreduce_cuda_layers(data, dtype, resolve_layers(numel, cfg_, env, explicit_bucket), average, env, stream,
+                            overlapped);
     } catch (...) {
       recording_ = nullptr;
       throw;
     }
     recording_ = nullptr;
+    if (fused_->generation() != gen_before) {
+      f.launches.clear();
+      return;
+    }
     f.registry_version = ver;
     f.plan_generation = fused_->generation();
     f.numel = numel;
@@ -168,10 +176,12 @@ void AllreduceEngine::allreduce_cuda(void* data, int dtype, int64_t numel, bool 
     f.env_bits = env.bits;
     f.env_bucket = env.bucket_size;
     f.skip_incomplete = env.skip_incomplete;
+    f.overlapped = overlapped;
     f.launches = std::move(rec);
     return;
   }
-  allreduce_cuda_layers(data, dtype, resolve_layers(numel, cfg_, env, explicit_bucket), average, env, stream);
+  allreduce_cuda_layers(data, dtype, resolve_layers(numel, cfg_, env, explicit_bucket), average, env, stream,
+                        overlapped);
 }
 
 void AllreduceEngine::allreduce_cpu(void* data, int dtype, int64_t numel, bool average, int explicit_bucket) {
@@ -182,11 +192,19 @@ void AllreduceEngine::allreduce_cpu(void* data, int dtype, int64_t numel, bool a
 }
 
 void AllreduceEngine::allreduce_cuda_layers(void* data, int dtype, const std::vector<LayerSpec>& layers_in,
-                                            bool average, const CompressionEnv& env, cudaStream_t stream) {
+                                            bool average, const CompressionEnv& env, cudaStream_t stream,
+                                            bool overlapped) {
   const bool need_fused = cfg_.inner_comm == CommType::kP2P && local_size_ > 0;
   if (need_fused && !fused_) throw std::runtime_error("cgx: P2P path is not initialised");
   if (fused_) fused_->check_status();
-  run_layers(true, data, dtype, layers_in, average, env, stream);
+  lane_cap_ = overlapped ? cfg_.overlap_lanes : 0;
+  try {
+    run_layers(true, data, dtype, layers_in, average, env, stream);
+  } catch (...) {
+    lane_cap_ = 0;
+    throw;
+  }
+  lane_cap_ = 0;
 }
 
 // One node-local allreduce of a fusion group: fused P2P kernel when available,
@@ -204,7 +222,7 @@ void AllreduceEngine::intra_stage(bool cuda, void* data, int dtype, const std::v
       uint64_t n = 0;
       for (const LayerSpec& l : group) n += l.numel;
       if ((int64_t)(n * (uint64_t)elsize) <= cfg_.oneshot_max_bytes) {
-        const DevicePlan* dp = fused_->prepare_oneshot(group, dtype, skip_incomplete, stream);
+        const DevicePlan* dp = fused_->prepare_oneshot(group, dtype, skip_incomplete, stream, lane_cap_);
         // every rank pushes its whole packed image to W-1 peers: keep that egress small
         if (dp != nullptr && dp->plan.total_wire * (uint64_t)(fused_->world() - 1) <= (4ull << 20)) {
           launch_fused(Launch{dp, true, 0u}, data, prescale, rng, stream);
@@ -218,7 +236,7 @@ void AllreduceEngine::intra_stage(bool cuda, void* data, int dtype, const std::v
     while (!todo.empty()) {
       std::vector<LayerSpec> gl = std::move(todo.back());
       todo.pop_back();
-      const DevicePlan* dp = fused_->prepare(gl, dtype, skip_incomplete, stream);
+      const DevicePlan* dp = fused_->prepare(gl, dtype, skip_incomplete, stream, lane_cap_);
       if (dp == nullptr) {
         if (gl.size() > 1) {
           size_t half = gl.size() / 2;

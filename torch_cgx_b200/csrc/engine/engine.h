@@ -85,11 +85,13 @@ class AllreduceEngine {
 
   // In-place SUM (or AVG) allreduce of a CUDA buffer on `stream`.
   //  explicit_bucket: DDP bucket index if the caller knows it, else -1.
+  //  overlapped: the call runs concurrently with compute (DDP hook) -> use at most
+  //  cfg.overlap_lanes CTAs instead of the whole GPU.
   void allreduce_cuda(void* data, int dtype, int64_t numel, bool average, int explicit_bucket,
-                      cudaStream_t stream);
+                      cudaStream_t stream, bool overlapped = false);
   // Same, with an explicit layer list (offsets relative to `data`).
   void allreduce_cuda_layers(void* data, int dtype, const std::vector<LayerSpec>& layers, bool average,
-                             const CompressionEnv& env, cudaStream_t stream);
+                             const CompressionEnv& env, cudaStream_t stream, bool overlapped = false);
 
   void check_health();
   const EngineStats& stats() const { return stats_; }
@@ -116,6 +118,7 @@ class AllreduceEngine {
     int dtype = -1;
     int env_bits = 0, env_bucket = 0;
     bool skip_incomplete = false;
+    bool overlapped = false;
     std::vector<Launch> launches;
   };
   std::vector<BucketFast> fast_;
@@ -129,6 +132,7 @@ class AllreduceEngine {
   std::unique_ptr<SymmetricHeap> heap_;
   std::unique_ptr<FusedSra> fused_;
   uint32_t call_seq_ = 0;
+  int lane_cap_ = 0;  // lane cap of the call being issued (0 = none)
   EngineStats stats_;
 };
 

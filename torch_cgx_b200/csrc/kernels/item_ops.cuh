@@ -1,0 +1,508 @@
+// Item-level operations built from item_path.cuh. Each function is executed by ONE warp on ONE
+// item; the hot (full-slice) versions are force-inlined templates, the cold (generic bucket,
+// raw tail) versions are deliberately out of line so that the hot loops stay a few hundred
+// instructions long.
+//
+//   *_send     quantize my values of an item and store the packed words to a destination set
+//              (SRA phase A, one-shot phase 1, standalone quantize)
+//   *_reduce   own values + the decoded copies of W-1 sources, requantize, publish, self-decode
+//              (SRA phase B)
+//   *_recv     decode one source -- or the sum of all sources -- into the gradient buffer
+//              (SRA phase C, one-shot phase 2, standalone dequantize)
+// Reference counterparts: Compressor::Compress / Decompress per layer slice
+// (/root/reference/src/common/compressor.cc:98-179) and the SRA loop bodies
+// (/root/reference/src/common/scatter_reduce_allgather.cc:116-199).
+#pragma once
+#include "item_path.cuh"
+
+namespace cgx {
+namespace dev {
+
+template <int GPL>
+struct SliceCfg {
+  static constexpr uint32_t kElems = 256u * GPL;
+  static constexpr uint32_t kLgAll = GPL == 4 ? 7u : 6u;  // log2(bucket/8) of a bucket spanning the slice
+  static constexpr int kPeerBatch = GPL == 4 ? 2 : 4;     // sources fetched before any is consumed
+};
+
+// ---- slice <-> registers -------------------------------------------------------------
+template <typename TS, int GPL>
+__device__ __forceinline__ void slice_load(const TS* __restrict__ src, float prescale, float (&x)[GPL][8]) {
+  const TS* p = src + lane_id() * 8u;
+  if (group_aligned<TS>(src)) {
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) load8_vec<TS>(p + k * 256, x[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) load8_scalar<TS>(p + k * 256, 8, x[k]);
+  }
+  if (prescale != 1.0f) {
+#pragma unroll
+    for (int k = 0; k < GPL; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[k][j] = __fmul_rn(x[k][j], prescale);
+  }
+}
+
+template <typename TO, int GPL>
+__device__ __forceinline__ void slice_store(TO* __restrict__ dst, const float (&x)[GPL][8]) {
+  TO* p = dst + lane_id() * 8u;
+  if (group_aligned<TO>(dst)) {
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) store8_vec<TO>(p + k * 256, x[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) store8_scalar<TO>(p + k * 256, 8, x[k]);
+  }
+}
+
+// per-bucket {unit, min} and 1/unit of every group row of the slice
+template <int GPL>
+__device__ __forceinline__ void slice_meta(const float (&x)[GPL][8], uint32_t lg, int bits, BucketMeta (&m)[GPL],
+                                           float (&inv)[GPL]) {
+  float mn[GPL], mx[GPL];
+#pragma unroll
+  for (int k = 0; k < GPL; ++k) {
+    mn[k] = CGX_INF_POS;
+    mx[k] = CGX_INF_NEG;
+    minmax8(x[k], mn[k], mx[k]);
+  }
+  if (GPL == 4 || lg == SliceCfg<GPL>::kLgAll) {  // one bucket == the slice (512 / 1024): the common case
+    float a = mn[0], b = mx[0];
+#pragma unroll
+    for (int k = 1; k < GPL; ++k) {
+      a = nan_min(a, mn[k]);
+      b = nan_max(b, mx[k]);
+    }
+    warp_minmax(a, b);
+    const BucketMeta m0 = make_meta(a, b, bits);
+    const float i0 = inv_unit(m0.unit);
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) {
+      m[k] = m0;
+      inv[k] = i0;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) {
+      if (lg >= 5)
+        warp_minmax(mn[k], mx[k]);
+      else
+        subwarp_minmax(mn[k], mx[k], lg);
+      m[k] = make_meta(mn[k], mx[k], bits);
+      inv[k] = inv_unit(m[k].unit);
+    }
+  }
+}
+
+template <int GPL>
+__device__ __forceinline__ void slice_store_meta(const BucketMeta (&m)[GPL], uint32_t lg, const DstSet& ds,
+                                                 uint32_t meta_off) {
+  if (GPL == 4 || lg == SliceCfg<GPL>::kLgAll) {
+    if (lane_id() == 0) dst_st_v2(ds, meta_off, __float_as_uint(m[0].unit), __float_as_uint(m[0].min));
+  } else {
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) {
+      const uint32_t gi = (uint32_t)k * 32u + lane_id();
+      if ((gi & ((1u << lg) - 1u)) == 0)
+        dst_st_v2(ds, meta_off + (gi >> lg) * 8u, __float_as_uint(m[k].unit), __float_as_uint(m[k].min));
+    }
+  }
+}
+
+// quantize + pack + store the slice; SELF: also write the decoded values (what every receiver
+// will decode from the same bytes) to `self_out`
+template <typename TO, int KB, int GPL, bool SELF, bool STOCH>
+__device__ __forceinline__ void slice_encode(const float (&x)[GPL][8], const BucketMeta (&m)[GPL],
+                                             const float (&inv)[GPL], int bits, const RngKey& rng,
+                                             uint32_t first_elem, const DstSet& ds, uint32_t pay_off,
+                                             TO* __restrict__ self_out) {
+  const float maxlvl = (float)max_level(bits);
+  const bool self_vec = SELF && group_aligned<TO>(self_out);
+  // every bucket of the slice has finite min/max (unit finite <=> max - min finite) -> no clamp
+  bool finite = true;
+#pragma unroll
+  for (int k = 0; k < GPL; ++k) finite = finite && (fabsf(m[k].unit) < CGX_INF_POS);
+  finite = __all_sync(kAll, finite);
+#pragma unroll
+  for (int k = 0; k < GPL; ++k) {
+    const uint32_t gi = (uint32_t)k * 32u + lane_id();
+    float u[8];
+    if (STOCH) {
+      float r[8];
+      rounding8(rng, first_elem + gi * 8u, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = level_magic<true>(x[k][j], m[k].min, inv[k], r[j], maxlvl);
+    } else if (finite) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = level_magic<false>(x[k][j], m[k].min, inv[k], 0.5f, maxlvl);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = level_magic<true>(x[k][j], m[k].min, inv[k], 0.5f, maxlvl);
+    }
+    uint32_t lo, hi;
+    pack_magic<KB>(u, bits, lo, hi);
+    store_word<KB>(ds, pay_off, gi, bits, lo, hi);
+    if (SELF) {
+      float dec[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dec[j] = __fmaf_rn(m[k].unit, __fsub_rn(u[j], CGX_MAGIC), m[k].min);
+      if (self_vec)
+        store8_vec<TO>(self_out + gi * 8u, dec);
+      else
+        store8_scalar<TO>(self_out + gi * 8u, 8, dec);
+    }
+  }
+}
+
+// issue the loads of one source's packed words + meta for the slice (no use yet)
+template <int KB, int GPL>
+__device__ __forceinline__ void slice_fetch(const uint8_t* rec, uint32_t meta_off, uint32_t pay_off, uint32_t lg,
+                                            int bits, uint32_t (&lo)[GPL], uint32_t (&hi)[GPL],
+                                            BucketMeta (&pm)[GPL]) {
+#pragma unroll
+  for (int k = 0; k < GPL; ++k) load_word<KB>(rec + pay_off, (uint32_t)k * 32u + lane_id(), bits, lo[k], hi[k]);
+  if (GPL == 4 || lg == SliceCfg<GPL>::kLgAll) {
+    const uint2 v = ld_sys_v2(rec + meta_off);
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) {
+      pm[k].unit = __uint_as_float(v.x);
+      pm[k].min = __uint_as_float(v.y);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) {
+      const uint2 v = ld_sys_v2(rec + meta_off + ((((uint32_t)k * 32u + lane_id()) >> lg) * 8u));
+      pm[k].unit = __uint_as_float(v.x);
+      pm[k].min = __uint_as_float(v.y);
+    }
+  }
+}
+
+// x (+)= decode(words)
+template <int KB, int GPL, bool ADD>
+__device__ __forceinline__ void slice_decode(const uint32_t (&lo)[GPL], const uint32_t (&hi)[GPL],
+                                             const BucketMeta (&pm)[GPL], int bits, float (&x)[GPL][8]) {
+#pragma unroll
+  for (int k = 0; k < GPL; ++k) {
+    float qf[8];
+    unpack_magic<KB>(lo[k], hi[k], bits, qf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = __fmaf_rn(pm[k].unit, qf[j], pm[k].min);
+      x[k][j] = ADD ? __fadd_rn(x[k][j], d) : d;
+    }
+  }
+}
+
+// x += decode(source i) for every source of the set, in slot order, `kPeerBatch` loads in flight
+template <int KB, int GPL>
+__device__ __forceinline__ void slice_accumulate(const SrcSet& ss, uint32_t meta_off, uint32_t pay_off, uint32_t lg,
+                                                 int bits, float (&x)[GPL][8]) {
+  constexpr int kB = SliceCfg<GPL>::kPeerBatch;
+  const int cnt = ss.n - (ss.skip >= 0 ? 1 : 0);
+  for (int i0 = 0; i0 < cnt; i0 += kB) {
+    uint32_t lo[kB][GPL], hi[kB][GPL];
+    BucketMeta pm[kB][GPL];
+#pragma unroll
+    for (int u = 0; u < kB; ++u) {
+      const int i = i0 + u;
+      if (i < cnt) {
+        const int q = (ss.skip >= 0 && i >= ss.skip) ? i + 1 : i;
+        slice_fetch<KB, GPL>(ss.base + (size_t)q * ss.stride, meta_off, pay_off, lg, bits, lo[u], hi[u], pm[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kB; ++u)
+      if (i0 + u < cnt) slice_decode<KB, GPL, true>(lo[u], hi[u], pm[u], bits, x);
+  }
+}
+
+// ======================================================================================
+// full items
+// ======================================================================================
+// TS: element type of the source, TO: element type of the self-decoded output (SELF only)
+template <typename TS, typename TO, int KB, int GPL, bool SELF>
+__device__ __forceinline__ void full_send(const TS* __restrict__ src, const WarpItem& it, float prescale,
+                                          const RngKey& rng, const DstSet& ds, TO* __restrict__ self_out) {
+  const int bits = KB ? KB : item_bits(it);
+  const uint32_t lg = item_lpb_log2(it);
+  float x[GPL][8];
+  slice_load<TS, GPL>(src, prescale, x);
+  BucketMeta m[GPL];
+  float inv[GPL];
+  slice_meta<GPL>(x, lg, bits, m, inv);
+  slice_store_meta<GPL>(m, lg, ds, it.meta_off);
+  if (rng.enabled)
+    slice_encode<TO, KB, GPL, SELF, true>(x, m, inv, bits, rng, it.elem_off, ds, it.pay_off, self_out);
+  else
+    slice_encode<TO, KB, GPL, SELF, false>(x, m, inv, bits, rng, it.elem_off, ds, it.pay_off, self_out);
+}
+
+template <typename T, int KB, int GPL>
+__device__ __forceinline__ void full_reduce(T* __restrict__ blk, const WarpItem& it, float prescale,
+                                            const RngKey& rng, const SrcSet& ss, const DstSet& ds) {
+  const int bits = KB ? KB : item_bits(it);
+  const uint32_t lg = item_lpb_log2(it);
+  float x[GPL][8];
+  slice_load<T, GPL>(blk, prescale, x);
+  slice_accumulate<KB, GPL>(ss, it.meta_off, it.pay_off, lg, bits, x);
+  BucketMeta m[GPL];
+  float inv[GPL];
+  slice_meta<GPL>(x, lg, bits, m, inv);
+  slice_store_meta<GPL>(m, lg, ds, it.meta_off);
+  if (rng.enabled)
+    slice_encode<T, KB, GPL, true, true>(x, m, inv, bits, rng, it.elem_off, ds, it.pay_off, blk);
+  else
+    slice_encode<T, KB, GPL, true, false>(x, m, inv, bits, rng, it.elem_off, ds, it.pay_off, blk);
+}
+
+// out = decode(one source)            (ss.n == 1)
+// out = sum of all sources, slot order (one-shot)
+template <typename TO, int KB, int GPL>
+__device__ __forceinline__ void full_recv(const SrcSet& ss, const WarpItem& it, TO* __restrict__ out) {
+  const int bits = KB ? KB : item_bits(it);
+  const uint32_t lg = item_lpb_log2(it);
+  float x[GPL][8];
+  if (ss.n == 1) {
+    uint32_t lo[GPL], hi[GPL];
+    BucketMeta pm[GPL];
+    slice_fetch<KB, GPL>(ss.base, it.meta_off, it.pay_off, lg, bits, lo, hi, pm);
+    slice_decode<KB, GPL, false>(lo, hi, pm, bits, x);
+  } else {
+#pragma unroll
+    for (int k = 0; k < GPL; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[k][j] = 0.f;
+    slice_accumulate<KB, GPL>(ss, it.meta_off, it.pay_off, lg, bits, x);
+  }
+  slice_store<TO, GPL>(out, x);
+}
+
+// ======================================================================================
+// generic bucket items (cold): ONE bucket of n <= kMaxBlockElems elements, any alignment,
+// any bit width. Two passes (min/max, then encode); lane l handles groups l, l+32, ...
+// ======================================================================================
+template <typename TS>
+__device__ __forceinline__ void bucket_load_group(const TS* __restrict__ src, uint32_t g, uint32_t n, float prescale,
+                                                  float (&x)[8], int& nv) {
+  nv = (int)min(8u, n - g * 8u);
+  load8_scalar<TS>(src + g * 8u, nv, x);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = __fmul_rn(x[j], prescale);
+}
+
+__device__ __forceinline__ void bucket_add_sources(const SrcSet& ss, const WarpItem& it, uint32_t g, int bits,
+                                                   float (&x)[8]) {
+  for (int q = 0; q < ss.n; ++q) {
+    if (q == ss.skip) continue;
+    const uint8_t* rec = ss.base + (size_t)q * ss.stride;
+    uint32_t lo, hi;
+    load_word<0>(rec + it.pay_off, g, bits, lo, hi);
+    const uint2 mv = ld_sys_v2(rec + it.meta_off);
+    float qf[8];
+    unpack_magic<0>(lo, hi, bits, qf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      x[j] = __fadd_rn(x[j], __fmaf_rn(__uint_as_float(mv.x), qf[j], __uint_as_float(mv.y)));
+  }
+}
+
+// phase A / phase B / quantize of a generic bucket. `ss.n == 0`: nothing to add (send);
+// self_out != nullptr: write the self-decoded values there
+template <typename TS, typename TO>
+__device__ __noinline__ void bucket_quantize(const TS* __restrict__ src, const WarpItem it, float prescale,
+                                             const RngKey rng, const SrcSet ss, const DstSet ds,
+                                             TO* __restrict__ self_out) {
+  const uint32_t n = item_n(it);
+  const int bits = item_bits(it);
+  const uint32_t ng = div_up(n, 8u);
+  float mn = CGX_INF_POS, mx = CGX_INF_NEG;
+  for (uint32_t g = lane_id(); g < ng; g += 32) {
+    float x[8];
+    int nv;
+    bucket_load_group<TS>(src, g, n, prescale, x, nv);
+    if (ss.n > 0) bucket_add_sources(ss, it, g, bits, x);
+    minmax8_pred(x, nv, mn, mx);
+  }
+  warp_minmax(mn, mx);
+  const BucketMeta m = make_meta(mn, mx, bits);
+  const float inv = inv_unit(m.unit);
+  const float maxlvl = (float)max_level(bits);
+  // generic items always use the unicast mappings (sub-word stores have no multimem form)
+  DstSet du = ds;
+  du.mc = nullptr;
+  if (lane_id() == 0) dst_st_v2(du, it.meta_off, __float_as_uint(m.unit), __float_as_uint(m.min));
+  for (uint32_t g = lane_id(); g < ng; g += 32) {
+    float x[8];
+    int nv;
+    bucket_load_group<TS>(src, g, n, prescale, x, nv);
+    if (ss.n > 0) bucket_add_sources(ss, it, g, bits, x);
+    float r[8];
+    if (rng.enabled) {
+      rounding8(rng, it.elem_off + g * 8u, r);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = 0.5f;
+    }
+    float u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = (j < nv) ? level_magic<true>(x[j], m.min, inv, r[j], maxlvl) : CGX_MAGIC;
+    uint32_t lo, hi;
+    pack_magic<0>(u, bits, lo, hi);
+    store_word<0>(du, it.pay_off, g, bits, lo, hi);
+    if (self_out != nullptr) {
+      float dec[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dec[j] = __fmaf_rn(m.unit, __fsub_rn(u[j], CGX_MAGIC), m.min);
+      store8_scalar<TO>(self_out + g * 8u, nv, dec);
+    }
+  }
+}
+
+// decode one source (ss.n == 1) or the sum of all sources into `out`
+template <typename TO>
+__device__ __noinline__ void bucket_recv(const SrcSet ss, const WarpItem it, TO* __restrict__ out) {
+  const uint32_t n = item_n(it);
+  const int bits = item_bits(it);
+  const uint32_t ng = div_up(n, 8u);
+  for (uint32_t g = lane_id(); g < ng; g += 32) {
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    SrcSet s2 = ss;
+    s2.skip = -1;
+    bucket_add_sources(s2, it, g, bits, x);  // 0 + d == d exactly
+    store8_scalar<TO>(out + g * 8u, (int)min(8u, n - g * 8u), x);
+  }
+}
+
+// ======================================================================================
+// raw (uncompressed) items: n <= 512 elements travelling as T
+// ======================================================================================
+// 8 values -> 8 T on the wire (16 B-aligned records): 2 x 16 B for fp32, 1 x 16 B otherwise
+template <typename T>
+__device__ __forceinline__ void raw_wire_store(const DstSet& ds, uint32_t off, const float (&v)[8]) {
+  if (sizeof(T) == 4) {
+    dst_st_v4(ds, off, pack16<T>(v));
+    dst_st_v4(ds, off + 16u, pack16<T>(v + 4));
+  } else {
+    dst_st_v4(ds, off, pack16<T>(v));
+  }
+}
+template <typename T>
+__device__ __forceinline__ void raw_wire_load(const uint8_t* p, float (&v)[8]) {
+  if (sizeof(T) == 4) {
+    unpack16<T>(ld_sys_v4(p), v);
+    unpack16<T>(ld_sys_v4(p + 16), v + 4);
+  } else {
+    unpack16<T>(ld_sys_v4(p), v);
+  }
+}
+// what a receiver reads back: the value rounded to T
+template <typename T>
+__device__ __forceinline__ float round_to(float v) {
+  return DT<T>::to_float(DT<T>::from_float(v));
+}
+
+// Full raw item (512 elements). MODE 0: push (phase A / one-shot 1): dst <- T(src * prescale)
+//                               MODE 1: reduce (phase B): own + sum(sources) -> own, dst
+//                               MODE 2: receive: out <- source (ss.n == 1) or sum of all sources
+template <typename T, int MODE>
+__device__ __forceinline__ void raw_full(T* __restrict__ blk, const WarpItem& it, float prescale, const SrcSet& ss,
+                                         const DstSet& ds) {
+  float x[2][8];
+  if (MODE == 2) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[k][j] = 0.f;
+  } else {
+    slice_load<T, 2>(blk, prescale, x);
+  }
+  if (MODE != 0) {
+    for (int q = 0; q < ss.n; ++q) {
+      if (q == ss.skip) continue;
+      const uint8_t* rec = ss.base + (size_t)q * ss.stride + it.meta_off;
+      float v[2][8];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) raw_wire_load<T>(rec + ((uint32_t)k * 32u + lane_id()) * 8u * sizeof(T), v[k]);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[k][j] = __fadd_rn(x[k][j], v[k][j]);
+    }
+  }
+  if (MODE != 2) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) raw_wire_store<T>(ds, it.meta_off + ((uint32_t)k * 32u + lane_id()) * 8u * sizeof(T), x[k]);
+  }
+  if (MODE != 0) slice_store<T, 2>(blk, x);
+}
+
+// In-switch reduction of a full raw item (NVLS): every rank staged T(src * prescale) at the same
+// heap offset; the owner pulls the sum with multimem.ld_reduce and multicasts it back in place.
+template <typename T>
+__device__ __forceinline__ void raw_full_mc_reduce(T* __restrict__ blk, const WarpItem& it, uint8_t* mc_slot) {
+  constexpr uint32_t kVecs = 512u * sizeof(T) / 16u / 32u;  // 16 B vectors per lane: 4 (fp32) or 2
+  uint4 v[kVecs];
+#pragma unroll
+  for (uint32_t i = 0; i < kVecs; ++i) v[i] = mc_ld_reduce_v4<T>(mc_slot + it.meta_off + (i * 32u + lane_id()) * 16u);
+  const bool vec = (reinterpret_cast<uintptr_t>(blk) & 15u) == 0;
+#pragma unroll
+  for (uint32_t i = 0; i < kVecs; ++i) {
+    const uint32_t byte = (i * 32u + lane_id()) * 16u;
+    mc_st_v4(mc_slot + it.meta_off + byte, v[i]);
+    T* o = blk + byte / sizeof(T);
+    if (vec) {
+      *reinterpret_cast<uint4*>(o) = v[i];
+    } else {
+      const T* pe = reinterpret_cast<const T*>(&v[i]);
+#pragma unroll
+      for (uint32_t j = 0; j < 16u / sizeof(T); ++j) o[j] = pe[j];
+    }
+  }
+}
+
+// raw tail (< 512 elements) or anything the vector path cannot take: element-wise, cold
+template <typename T>
+__device__ __noinline__ void raw_tail(T* __restrict__ blk, const WarpItem it, float prescale, const SrcSet ss,
+                                      const DstSet ds, int mode) {
+  const uint32_t n = item_n(it);
+  DstSet du = ds;
+  du.mc = nullptr;
+  for (uint32_t i = lane_id(); i < n; i += 32) {
+    float x = mode == 2 ? 0.f : __fmul_rn(DT<T>::to_float(blk[i]), prescale);
+    if (mode != 0) {
+      for (int q = 0; q < ss.n; ++q) {
+        if (q == ss.skip) continue;
+        const T* rec = reinterpret_cast<const T*>(ss.base + (size_t)q * ss.stride + it.meta_off);
+        T v;
+        if (sizeof(T) == 4) {
+          const uint32_t b = ld_sys_u32(rec + i);
+          v = *reinterpret_cast<const T*>(&b);
+        } else {
+          const uint16_t b = (uint16_t)ld_sys_u16(rec + i);
+          v = *reinterpret_cast<const T*>(&b);
+        }
+        x = __fadd_rn(x, DT<T>::to_float(v));
+      }
+    }
+    const T t = DT<T>::from_float(x);
+    if (mode != 2) {
+      for (int q = 0; q <= du.n; ++q) {
+        // q == n: the optional extra local copy
+        if (q == du.skip || (q == du.n && du.local == nullptr)) continue;
+        T* d = reinterpret_cast<T*>((q == du.n ? du.local : du.bases[q]) + du.off + it.meta_off) + i;
+        if (sizeof(T) == 4)
+          st_u32(d, *reinterpret_cast<const uint32_t*>(&t));
+        else
+          st_u16(d, *reinterpret_cast<const uint16_t*>(&t));
+      }
+    }
+    if (mode != 0) blk[i] = t;
+  }
+}
+
+}  // namespace dev
+}  // namespace cgx

@@ -1,0 +1,362 @@
+// The product: ONE kernel per fusion buffer that performs the whole compressed
+// Scatter-Reduce-AllGather allreduce over NVLink 5 / NVSwitch.
+//
+//   phase A  for every peer p: quantize my copy of chunk p item by item and store the packed
+//            words straight into p's receive slot (peer-mapped st.global), then ONE system-scope
+//            release per lane
+//   phase B  acquire the W-1 incoming copies of MY chunk, dequantize + accumulate them with my
+//            raw values in fp32 registers, requantize, publish the packed result to every rank
+//            -- ONE multimem.st into the NVLS multicast mapping when the heap has one, W-1 peer
+//            stores otherwise -- and write the self-decoded values to my gradient buffer
+//   phase C  acquire each peer's reduced chunk (in order of arrival), dequantize into my buffer
+//
+// The grid is G persistent *lanes* (CTAs of 8 warps, two per SM). Lane c of every rank only ever
+// talks to lane c of the other ranks through single-writer epoch flags, so there is no grid-wide
+// or host synchronisation anywhere and lanes pipeline independently. The work of a lane is a
+// flat list of warp items (common/wire.h) dealt round-robin to its warps; the hot loops contain
+// only the full-slice path (item_ops.cuh), everything rare is out of line.
+//
+// The epoch lives in device memory (DeviceSync): the kernel is CUDA-graph capturable.
+//
+// Uncompressed layers ride the same launch as raw items: the classic two-shot P2P allreduce with
+// the 1/W prescale fused, or -- with a multicast heap -- an in-switch reduction
+// (multimem.ld_reduce + multimem.st), the NVLS algorithm of NCCL inside our kernel.
+//
+// Reference behaviour being replaced (4-5 launches per layer + host polling):
+//   /root/reference/src/common/scatter_reduce_allgather.cc:94-202 (compressed), :308-413 (raw)
+//   /root/reference/src/common/nccl_reduce.cc:103-198
+//   /root/reference/src/common/shm_communicator.cc:110-177
+#pragma once
+#include "item_ops.cuh"
+#include "launch.h"
+
+namespace cgx {
+namespace dev {
+
+// Tracing: per-lane phase timestamps (slot 0: kernel start [min], 1: phase A done,
+// 2: phase B inputs arrived, 3: phase B done, 4: last phase-C wait satisfied, 5: end [max]).
+__device__ __forceinline__ void trace_mark(unsigned long long* trace, int lane, int slot, bool is_min = false) {
+  if (trace == nullptr || (threadIdx.x & 31u) != 0) return;
+  const unsigned long long t = globaltimer_ns();
+  if (is_min)
+    atomicMin(&trace[(size_t)lane * 8 + slot], t);
+  else
+    atomicMax(&trace[(size_t)lane * 8 + slot], t);
+}
+
+// Every CTA reads the epoch before any CTA can have bumped it: the bump happens after ALL CTAs
+// of the launch have passed their read (each counts itself as finished only at its very end).
+__device__ __forceinline__ void sync_finish(DeviceSync* sync, uint32_t epoch, int lanes) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&sync->finished, 1u) + 1u == (uint32_t)lanes) {
+      sync->finished = 0;
+      sync->epoch = epoch;
+      __threadfence();
+    }
+  }
+}
+
+// warp 0: publish "this lane finished the phase" to every peer. One fence.acq_rel.sys drains the
+// NVLink stores of the whole CTA (made visible to this warp by the preceding bar.sync).
+__device__ __forceinline__ void signal_peers(uint32_t* const* flags, int W, int r, uint32_t flag_stride, int lane,
+                                             uint32_t epoch) {
+  const uint32_t wl = lane_id();
+  if (wl < (uint32_t)W && (int)wl != r) st_release_sys(flags[wl] + (size_t)r * flag_stride + lane, epoch);
+}
+
+// warp 0: wait until every peer's flag for this lane reached the epoch. Returns false on timeout.
+__device__ __forceinline__ bool wait_peers(const uint32_t* my_flags, int W, int r, uint32_t flag_stride, int lane,
+                                           uint32_t epoch, uint64_t timeout_ns, uint32_t* status, uint32_t code) {
+  const uint32_t wl = lane_id();
+  bool ok = true;
+  if (wl < (uint32_t)W && (int)wl != r) {
+    ok = wait_flag(my_flags + (size_t)wl * flag_stride + lane, epoch, timeout_ns);
+    if (!ok) *status = code | (wl << 8) | ((uint32_t)lane << 16);
+  }
+  return __all_sync(kAll, ok);
+}
+
+template <typename T, int KB, int GPL>
+__global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const __grid_constant__ SraParams p) {
+  __shared__ int s_abort;
+  const int lane = blockIdx.x;
+  const int r = p.rank, W = p.world, G = p.lanes;
+  const uint32_t warp = threadIdx.x >> 5, wl = threadIdx.x & 31u;
+  T* data = reinterpret_cast<T*>(p.data);
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(&p.sync->epoch) + 1u;
+  RngKey rng = p.rng;
+  rng.seq += epoch - p.epoch_hint;  // graph replays advance the random stream
+  if (threadIdx.x == 0) s_abort = 0;
+  __syncthreads();
+  trace_mark(p.trace, lane, 0, true);
+
+  const SrcSet no_src{nullptr, 0u, 0, -1};
+
+  // ------------------------------------------------------------------ phase A
+  {
+    rng.stream = (uint32_t)r * 2u;
+    uint32_t base = 0;  // items dealt so far: item i of the phase goes to warp (i % kSraWarps)
+    // with the in-switch reduction my own chunk's full raw items are staged too
+    for (int s = p.mc_reduce ? 0 : 1; s < W; ++s) {
+      const int dstp = (r + s) % W;
+      const uint32_t i0 = p.item_first[dstp * G + lane];
+      const uint32_t cnt = p.item_first[dstp * G + lane + 1] - i0;
+      const DstSet push{&p.recv1[dstp], nullptr, (uint32_t)r * p.slot_bytes, 1, -1, nullptr};
+      const DstSet stage{&p.recv2[r], nullptr, (uint32_t)dstp * p.slot_bytes, 1, -1, nullptr};
+      for (uint32_t i = (warp - base) & (kSraWarps - 1); i < cnt; i += kSraWarps) {
+        const WarpItem it = p.items[i0 + i];
+        const uint32_t kind = item_kind(it);
+        T* blk = data + it.elem_off;
+        if (p.mc_reduce) {
+          if (kind == kItemRaw) {
+            raw_full<T, 0>(blk, it, p.prescale, no_src, stage);
+            continue;
+          }
+          if (s == 0) continue;
+        }
+        if (kind == kItemFull)
+          full_send<T, T, KB, GPL, false>(blk, it, p.prescale, rng, push, nullptr);
+        else if (kind == kItemRaw)
+          raw_full<T, 0>(blk, it, p.prescale, no_src, push);
+        else if (kind == kItemBucket)
+          bucket_quantize<T, T>(blk, it, p.prescale, rng, no_src, push, nullptr);
+        else
+          raw_tail<T>(blk, it, p.prescale, no_src, push, 0);
+      }
+      base += cnt;
+    }
+    __syncthreads();
+    if (warp == 0) signal_peers(p.flags1, W, r, p.flag_stride, lane, epoch);
+  }
+  trace_mark(p.trace, lane, 1);
+
+  // ------------------------------------------------------------------ phase B
+  {
+    const uint32_t i0 = p.item_first[r * G + lane];
+    const uint32_t cnt = p.item_first[r * G + lane + 1] - i0;
+    if (warp == 0 && cnt > 0) {
+      if (!wait_peers(p.flags1[r], W, r, p.flag_stride, lane, epoch, p.timeout_ns, p.status, kSraTimeoutPhase1))
+        s_abort = 1;
+    }
+    __syncthreads();
+    trace_mark(p.trace, lane, 2);
+    if (!s_abort) {
+      rng.stream = (uint32_t)r * 2u + 1u;
+      const SrcSet ss{p.recv1[r], p.slot_bytes, W, r};
+      const DstSet ds{p.recv2, p.mc_recv2, (uint32_t)r * p.slot_bytes, W, r, nullptr};
+      for (uint32_t i = warp; i < cnt; i += kSraWarps) {
+        const WarpItem it = p.items[i0 + i];
+        const uint32_t kind = item_kind(it);
+        T* blk = data + it.elem_off;
+        if (kind == kItemFull)
+          full_reduce<T, KB, GPL>(blk, it, p.prescale, rng, ss, ds);
+        else if (kind == kItemRaw) {
+          if (p.mc_reduce)
+            raw_full_mc_reduce<T>(blk, it, p.mc_recv2 + (size_t)r * p.slot_bytes);
+          else
+            raw_full<T, 1>(blk, it, p.prescale, ss, ds);
+        } else if (kind == kItemBucket)
+          bucket_quantize<T, T>(blk, it, p.prescale, rng, ss, ds, blk);
+        else
+          raw_tail<T>(blk, it, p.prescale, ss, ds, 1);
+      }
+    }
+    __syncthreads();
+    if (warp == 0 && !s_abort) signal_peers(p.flags2, W, r, p.flag_stride, lane, epoch);
+  }
+  trace_mark(p.trace, lane, 3);
+
+  // ------------------------------------------------------------------ phase C
+  if (!s_abort) {
+    // lane s of every warp looks after chunk (r + s) % W: its item range and rotation
+    const int myq = (r + (int)wl) % W;
+    const bool mine = wl >= 1 && wl < (uint32_t)W;
+    const uint32_t my_i0 = mine ? p.item_first[myq * G + lane] : 0u;
+    const uint32_t my_cnt = mine ? p.item_first[myq * G + lane + 1] - my_i0 : 0u;
+    uint32_t pre = my_cnt;  // inclusive prefix sum over lanes -> rotation keeps the warps balanced
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(kAll, pre, o);
+      if ((int)wl >= o) pre += v;
+    }
+    const uint32_t my_rot = pre - my_cnt;
+    const uint32_t* my_flag = p.flags2[r] + (size_t)myq * p.flag_stride + lane;
+    uint32_t pending = __ballot_sync(kAll, my_cnt > 0);
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (pending) {
+      const bool rdy = ((pending >> wl) & 1u) && (int32_t)(ld_acquire_sys(my_flag) - epoch) >= 0;
+      uint32_t ready = __ballot_sync(kAll, rdy);
+      if (!ready) {
+        if ((++spins & 0x3FFu) == 0) {
+          const uint64_t now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          const bool expired = now - t0 > p.timeout_ns;
+          if (__any_sync(kAll, expired)) {
+            if (wl == (uint32_t)__ffs(pending) - 1u)
+              *p.status = kSraTimeoutPhase2 | ((uint32_t)myq << 8) | ((uint32_t)lane << 16);
+            break;
+          }
+        }
+        continue;
+      }
+      pending &= ~ready;
+      trace_mark(p.trace, lane, 4);
+      while (ready) {
+        const int s = __ffs(ready) - 1;
+        ready &= ready - 1;
+        const int q = (r + s) % W;
+        const uint32_t i0 = __shfl_sync(kAll, my_i0, s);
+        const uint32_t cnt = __shfl_sync(kAll, my_cnt, s);
+        const uint32_t rot = __shfl_sync(kAll, my_rot, s);
+        const SrcSet ss{p.recv2[r] + (size_t)q * p.slot_bytes, 0u, 1, -1};
+        for (uint32_t i = (warp - rot) & (kSraWarps - 1); i < cnt; i += kSraWarps) {
+          const WarpItem it = p.items[i0 + i];
+          const uint32_t kind = item_kind(it);
+          T* blk = data + it.elem_off;
+          if (kind == kItemFull)
+            full_recv<T, KB, GPL>(ss, it, blk);
+          else if (kind == kItemRaw)
+            raw_full<T, 2>(blk, it, 1.0f, ss, DstSet{nullptr, nullptr, 0u, 0, -1, nullptr});
+          else if (kind == kItemBucket)
+            bucket_recv<T>(ss, it, blk);
+          else
+            raw_tail<T>(blk, it, 1.0f, ss, DstSet{nullptr, nullptr, 0u, 0, -1, nullptr}, 2);
+        }
+      }
+    }
+  }
+  trace_mark(p.trace, lane, 5);
+  sync_finish(p.sync, epoch, G);
+}
+
+// ===========================================================================
+// One-shot allreduce for small / latency-bound messages: ONE signalling hop.
+// Every rank quantizes its WHOLE buffer once and stores the packed image into slot `rank` of
+// every rank's one-shot region (one multimem.st with NVLS); after one flag exchange every rank
+// decodes all W images in rank order and sums them in fp32. Replicas are bit-identical (same
+// bytes, same order) and each contribution is quantized exactly once. Costs W/2 x the wire bytes
+// of SRA, irrelevant below ~1 MB where latency dominates. (SURVEY.md build plan step 5; replaces
+// the reference's tiny-tensor all-to-all, /root/reference/src/common/reducer.cc:35-94.)
+// Consecutive calls alternate between two regions (epoch parity): a peer can be one call ahead.
+// ===========================================================================
+template <typename T, int KB, int GPL>
+__global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(const __grid_constant__ SraParams p) {
+  __shared__ int s_abort;
+  const int lane = blockIdx.x;
+  const int r = p.rank, W = p.world;
+  const uint32_t warp = threadIdx.x >> 5;
+  T* data = reinterpret_cast<T*>(p.data);
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(&p.sync->epoch) + 1u;
+  RngKey rng = p.rng;
+  rng.seq += epoch - p.epoch_hint;
+  rng.stream = (uint32_t)r * 2u;
+  if (threadIdx.x == 0) s_abort = 0;
+  __syncthreads();
+  trace_mark(p.trace, lane, 0, true);
+  const uint32_t region = (epoch & 1u) * p.os_parity_stride;
+  const uint32_t i0 = p.item_first[lane];
+  const uint32_t cnt = p.item_first[lane + 1] - i0;
+  const SrcSet no_src{nullptr, 0u, 0, -1};
+
+  // ---- phase 1: my image -> slot r of every rank (mine included)
+  {
+    // with NVLS the switch also delivers my own replica, but asynchronously: my slot is
+    // additionally written with a plain local store so that phase 2 never depends on the loopback
+    const DstSet ds{p.recv1, p.mc_recv1, region + (uint32_t)r * p.slot_bytes, W, p.mc_recv1 ? r : -1,
+                    p.mc_recv1 ? p.recv1[r] : nullptr};
+    for (uint32_t i = warp; i < cnt; i += kSraWarps) {
+      const WarpItem it = p.items[i0 + i];
+      const uint32_t kind = item_kind(it);
+      T* blk = data + it.elem_off;
+      if (kind == kItemFull)
+        full_send<T, T, KB, GPL, false>(blk, it, p.prescale, rng, ds, nullptr);
+      else if (kind == kItemRaw)
+        raw_full<T, 0>(blk, it, p.prescale, no_src, ds);
+      else if (kind == kItemBucket)
+        bucket_quantize<T, T>(blk, it, p.prescale, rng, no_src, ds, nullptr);
+      else
+        raw_tail<T>(blk, it, p.prescale, no_src, ds, 0);
+    }
+    __syncthreads();
+    if (warp == 0) signal_peers(p.flags1, W, r, p.flag_stride, lane, epoch);
+  }
+  trace_mark(p.trace, lane, 1);
+
+  // ---- phase 2: all W images (mine was written by this CTA, ordered by the bar.sync above)
+  {
+    if (warp == 0 && cnt > 0) {
+      if (!wait_peers(p.flags1[r], W, r, p.flag_stride, lane, epoch, p.timeout_ns, p.status, kSraTimeoutPhase1))
+        s_abort = 1;
+    }
+    __syncthreads();
+    trace_mark(p.trace, lane, 2);
+    if (!s_abort) {
+      const SrcSet ss{p.recv1[r] + region, p.slot_bytes, W, -1};
+      const DstSet none{nullptr, nullptr, 0u, 0, -1, nullptr};
+      for (uint32_t i = warp; i < cnt; i += kSraWarps) {
+        const WarpItem it = p.items[i0 + i];
+        const uint32_t kind = item_kind(it);
+        T* blk = data + it.elem_off;
+        if (kind == kItemFull)
+          full_recv<T, KB, GPL>(ss, it, blk);
+        else if (kind == kItemRaw)
+          raw_full<T, 2>(blk, it, 1.0f, ss, none);
+        else if (kind == kItemBucket)
+          bucket_recv<T>(ss, it, blk);
+        else
+          raw_tail<T>(blk, it, 1.0f, ss, none, 2);
+      }
+    }
+  }
+  trace_mark(p.trace, lane, 5);
+  sync_finish(p.sync, epoch, p.lanes);
+}
+
+}  // namespace dev
+
+// ---- host side: pick the instantiation --------------------------------------------------
+template <typename T, int KB, int GPL>
+cudaError_t launch_sra_inst(const SraParams& p, cudaStream_t stream) {
+  if (p.oneshot)
+    dev::oneshot_kernel<T, KB, GPL><<<p.lanes, kSraThreads, 0, stream>>>(p);
+  else
+    dev::sra_kernel<T, KB, GPL><<<p.lanes, kSraThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <typename T, int GPL>
+cudaError_t launch_sra_gpl(const SraParams& p, cudaStream_t stream) {
+  switch (p.uniform_bits) {
+    case 2: return launch_sra_inst<T, 2, GPL>(p, stream);
+    case 4: return launch_sra_inst<T, 4, GPL>(p, stream);
+    case 8: return launch_sra_inst<T, 8, GPL>(p, stream);
+    default: return launch_sra_inst<T, 0, GPL>(p, stream);
+  }
+}
+
+template <typename T>
+cudaError_t launch_sra_t(const SraParams& p, cudaStream_t stream) {
+  return p.slice_elems == 1024 ? launch_sra_gpl<T, 4>(p, stream) : launch_sra_gpl<T, 2>(p, stream);
+}
+
+template <typename T>
+int sra_resident_per_sm_t() {
+  int a = 0, b = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, dev::sra_kernel<T, 0, 2>, kSraThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, dev::sra_kernel<T, 0, 4>, kSraThreads, 0) != cudaSuccess)
+    return 0;
+  return a < b ? a : b;
+}
+
+// defined once per dtype in sra_{f32,f16,bf16}.cu
+cudaError_t launch_sra_f32(const SraParams& p, cudaStream_t stream);
+cudaError_t launch_sra_f16(const SraParams& p, cudaStream_t stream);
+cudaError_t launch_sra_bf16(const SraParams& p, cudaStream_t stream);
+int sra_resident_per_sm_f32();
+int sra_resident_per_sm_f16();
+int sra_resident_per_sm_bf16();
+
+}  // namespace cgx

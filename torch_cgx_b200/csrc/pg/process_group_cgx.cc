@@ -208,9 +208,7 @@ void ProcessGroupCGX::ensure_cuda(c10::DeviceIndex dev) {
   if (cfg_.inner_comm == CommType::kP2P) {
     // agree on the number of lanes (CTAs): min over the node's ranks of what can be co-resident
     int resident = sra_max_resident_ctas(kF32);
-    int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int want = cfg_.lanes > 0 ? cfg_.lanes : sms;
+    int want = cfg_.lanes > 0 ? cfg_.lanes : resident;
     int mine = std::max(1, std::min(want, resident));
     C10dKV kv(store_);
     const std::string prefix = "cgx/p2p/node" + std::to_string(node);
@@ -254,7 +252,7 @@ c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::engine_allreduce(at::Tensor& t, 
     // the caching allocator must not hand this memory out while the comm stream uses it
     c10::cuda::CUDACachingAllocator::recordStream(t.storage().data_ptr(), *comm_stream_);
     engine_->allreduce_cuda(t.data_ptr(), to_cgx_dtype(t.scalar_type()), t.numel(), average, bucket_idx,
-                            comm_stream_->stream());
+                            comm_stream_->stream(), /*overlapped=*/bucket_idx >= 0);
     work->finish_on_stream();
   }
   return work;

@@ -63,7 +63,7 @@ class CpuBackend : public BlockBackend {
 class CudaBackend : public BlockBackend {
  public:
   ~CudaBackend() override {
-    if (d_blocks_) cudaFree(d_blocks_);
+    if (d_items_) cudaFree(d_items_);
   }
   bool is_cuda() const override { return true; }
   void* alloc(size_t bytes) override {
@@ -74,46 +74,55 @@ class CudaBackend : public BlockBackend {
   }
   void release(void* p) override { cudaFree(p); }
   void bind(const Plan& plan, cudaStream_t stream) override {
+    if (plan_ == &plan) return;  // plans are cached by the reducers and immutable: upload once
     plan_ = &plan;
-    const size_t bytes = plan.blocks.size() * sizeof(BlockDesc);
+    const size_t bytes = plan.items.size() * sizeof(WarpItem);
     if (bytes > cap_) {
-      if (d_blocks_) {
+      if (d_items_) {
         cuda_check(cudaStreamSynchronize(stream), "sync before plan realloc");
-        cudaFree(d_blocks_);
+        cudaFree(d_items_);
       }
-      cuda_check(cudaMalloc((void**)&d_blocks_, bytes), "cudaMalloc(plan)");
+      cuda_check(cudaMalloc((void**)&d_items_, bytes), "cudaMalloc(plan)");
       cap_ = bytes;
     }
-    cuda_check(cudaMemcpyAsync(d_blocks_, plan.blocks.data(), bytes, cudaMemcpyHostToDevice, stream), "upload plan");
+    if (bytes)
+      cuda_check(cudaMemcpyAsync(d_items_, plan.items.data(), bytes, cudaMemcpyHostToDevice, stream), "upload plan");
   }
   void quantize(const void* src, uint32_t first, uint32_t count, uint8_t* wire, float prescale, const RngKey& rng,
                 cudaStream_t stream) override {
-    cuda_check(launch_quantize_blocks(src, plan_->dtype, d_blocks_, first, count, wire, prescale, rng, stream),
-               "quantize_blocks");
+    cuda_check(launch_quantize_items(args(first, count), src, wire, prescale, rng, stream), "quantize_items");
   }
   void accumulate(const uint8_t* wire, uint32_t first, uint32_t count, float* acc_f32, uint32_t base_elem,
                   const void* init_src, float prescale, cudaStream_t stream) override {
-    cuda_check(launch_accumulate_blocks_f32(wire, plan_->dtype, d_blocks_, first, count, acc_f32, base_elem, init_src,
-                                            prescale, stream),
-               "accumulate_blocks");
+    cuda_check(launch_accumulate_items_f32(args(first, count), wire, acc_f32, base_elem, init_src, prescale, stream),
+               "accumulate_items");
   }
   void quantize_f32(const float* acc_f32, uint32_t base_elem, uint32_t first, uint32_t count, uint8_t* wire,
                     const RngKey& rng, void* out, cudaStream_t stream) override {
-    cuda_check(launch_quantize_blocks_f32(acc_f32, base_elem, plan_->dtype, d_blocks_, first, count, wire, rng, out,
-                                          stream),
-               "quantize_blocks_f32");
+    cuda_check(launch_quantize_items_f32(args(first, count), acc_f32, base_elem, wire, rng, out, stream),
+               "quantize_items_f32");
   }
   void dequantize(const uint8_t* wire, uint32_t first, uint32_t count, void* dst, cudaStream_t stream) override {
-    cuda_check(launch_dequantize_blocks(wire, plan_->dtype, d_blocks_, first, count, dst, stream),
-               "dequantize_blocks");
+    cuda_check(launch_dequantize_items(args(first, count), wire, dst, stream), "dequantize_items");
   }
   void copy(void* dst, const void* src, size_t bytes, cudaStream_t stream) override {
     cuda_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream), "cudaMemcpyAsync");
   }
 
  private:
+  // blocks [first, first+count) -> their warp items (items are emitted block by block)
+  ItemKernelArgs args(uint32_t first, uint32_t count) const {
+    ItemKernelArgs a;
+    a.items = d_items_;
+    a.first = plan_->block_item_first[first];
+    a.count = plan_->block_item_first[first + count] - a.first;
+    a.dtype = plan_->dtype;
+    a.slice_elems = (int)plan_->slice_elems;
+    a.uniform_bits = plan_->uniform_bits;
+    return a;
+  }
   const Plan* plan_ = nullptr;
-  BlockDesc* d_blocks_ = nullptr;
+  WarpItem* d_items_ = nullptr;
   size_t cap_ = 0;
 };
 

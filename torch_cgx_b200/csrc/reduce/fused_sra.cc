@@ -1,5 +1,6 @@
 #include "fused_sra.h"
 
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -11,11 +12,10 @@ namespace cgx {
 FusedSra::FusedSra(SymmetricHeap* heap, int max_lanes, int64_t timeout_ms, uint32_t min_lane_elems)
     : heap_(heap), max_lanes_(max_lanes), timeout_ns_((uint64_t)timeout_ms * 1000000ull),
       min_lane_elems_(min_lane_elems) {
-  {
-    // CGX_KERNEL: "warp" (default: 16 warps/SM, 128 regs), "warp2" (32 warps/SM, 64 regs), "block" (v1)
-    const std::string k = env_str("CGX_KERNEL", "warp");
-    variant_ = k == "block" ? 1 : (k == "warp2" ? 2 : 0);
-  }
+  // NVLS: multimem.st for phase B / one-shot, multimem.ld_reduce for raw items (CGX_NVLS=0 disables
+  // the heap's multicast mapping altogether; CGX_NVLS_REDUCE=0 keeps the two-shot raw path)
+  use_mc_ = heap_->has_multicast() && heap_->world() > 1;
+  use_mc_reduce_ = use_mc_ && env_bool("CGX_NVLS_REDUCE", true);
   if (max_lanes_ < 1) max_lanes_ = 1;
   if ((uint32_t)max_lanes_ > heap_->layout().flag_stride) max_lanes_ = (int)heap_->layout().flag_stride;
 }
@@ -39,27 +39,27 @@ std::vector<uint64_t> FusedSra::read_trace() {
 FusedSra::~FusedSra() {
   if (d_trace_) cudaFree(d_trace_);
   for (auto& kv : cache_) {
-    if (kv.second->d_blocks) cudaFree(kv.second->d_blocks);
-    if (kv.second->d_lane_first) cudaFree(kv.second->d_lane_first);
+    if (kv.second->d_items) cudaFree(kv.second->d_items);
+    if (kv.second->d_item_first) cudaFree(kv.second->d_item_first);
   }
 }
 
 const DevicePlan* FusedSra::prepare(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
-                                    cudaStream_t stream) {
-  return prepare_impl(layers, dtype, skip_incomplete, stream, world(), heap_->layout().slot_bytes);
+                                    cudaStream_t stream, int max_lanes) {
+  return prepare_impl(layers, dtype, skip_incomplete, stream, world(), heap_->layout().slot_bytes, max_lanes);
 }
 
 const DevicePlan* FusedSra::prepare_oneshot(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
-                                            cudaStream_t stream) {
+                                            cudaStream_t stream, int max_lanes) {
   if (heap_->layout().os_slot_bytes == 0) return nullptr;
-  return prepare_impl(layers, dtype, skip_incomplete, stream, 1, heap_->layout().os_slot_bytes);
+  return prepare_impl(layers, dtype, skip_incomplete, stream, 1, heap_->layout().os_slot_bytes, max_lanes);
 }
 
 const DevicePlan* FusedSra::prepare_impl(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
-                                         cudaStream_t stream, int plan_world, uint32_t capacity) {
+                                         cudaStream_t stream, int plan_world, uint32_t capacity, int max_lanes) {
   PlanOptions opt;
   opt.world = plan_world;
-  opt.lanes = max_lanes_;
+  opt.lanes = (max_lanes > 0 && max_lanes < max_lanes_) ? max_lanes : max_lanes_;
   opt.dtype = dtype;
   opt.skip_incomplete = skip_incomplete;
   opt.min_lane_elems = min_lane_elems_;
@@ -71,30 +71,31 @@ const DevicePlan* FusedSra::prepare_impl(const std::vector<LayerSpec>& layers, i
       // old tables are ordered before the frees by the synchronize) and invalidate derived caches
       cuda_check(cudaStreamSynchronize(stream), "sync before trimming the plan cache");
       for (auto& kv : cache_) {
-        if (kv.second->d_blocks) cudaFree(kv.second->d_blocks);
-        if (kv.second->d_lane_first) cudaFree(kv.second->d_lane_first);
+        if (kv.second->d_items) cudaFree(kv.second->d_items);
+        if (kv.second->d_item_first) cudaFree(kv.second->d_item_first);
       }
       cache_.clear();
       ++generation_;
     }
     auto dp = std::make_unique<DevicePlan>();
     dp->plan = build_plan(layers, opt);
-    int ub = -1;
-    for (const BlockDesc& bd : dp->plan.blocks) {
-      if (block_is_raw(bd)) continue;
-      const int bb = block_bits(bd);
-      ub = (ub == -1 || ub == bb) ? bb : 0;
+    {
+      bool ok = true;
+      for (const BlockDesc& bd : dp->plan.blocks) {
+        const int bb = block_bits(bd);
+        ok = ok && (block_is_raw(bd) || bb == 2 || bb == 4 || bb == 8);
+      }
+      dp->multicast_ok = ok;
     }
-    dp->uniform_bits = ub > 0 ? ub : 0;
-    if (dp->plan.max_chunk_wire <= capacity && !dp->plan.blocks.empty()) {
-      const size_t bb = dp->plan.blocks.size() * sizeof(BlockDesc);
-      const size_t lb = dp->plan.lane_first.size() * sizeof(uint32_t);
-      cuda_check(cudaMalloc((void**)&dp->d_blocks, bb), "cudaMalloc(plan blocks)");
-      cuda_check(cudaMalloc((void**)&dp->d_lane_first, lb), "cudaMalloc(plan lanes)");
+    if (dp->plan.max_chunk_wire <= capacity && !dp->plan.items.empty()) {
+      const size_t ib = dp->plan.items.size() * sizeof(WarpItem);
+      const size_t fb = dp->plan.item_first.size() * sizeof(uint32_t);
+      cuda_check(cudaMalloc((void**)&dp->d_items, ib), "cudaMalloc(plan items)");
+      cuda_check(cudaMalloc((void**)&dp->d_item_first, fb), "cudaMalloc(plan lanes)");
       // pageable source: the runtime stages it before returning, so the vectors may be reused
-      cuda_check(cudaMemcpyAsync(dp->d_blocks, dp->plan.blocks.data(), bb, cudaMemcpyHostToDevice, stream),
-                 "upload plan blocks");
-      cuda_check(cudaMemcpyAsync(dp->d_lane_first, dp->plan.lane_first.data(), lb, cudaMemcpyHostToDevice, stream),
+      cuda_check(cudaMemcpyAsync(dp->d_items, dp->plan.items.data(), ib, cudaMemcpyHostToDevice, stream),
+                 "upload plan items");
+      cuda_check(cudaMemcpyAsync(dp->d_item_first, dp->plan.item_first.data(), fb, cudaMemcpyHostToDevice, stream),
                  "upload plan lanes");
     }
     if (log_level() >= 2) log_msg(2, "cgx[%d]: new plan %s", rank(), describe_plan(dp->plan).c_str());
@@ -117,32 +118,38 @@ void FusedSra::run_oneshot(const DevicePlan& dp, void* data, float prescale, con
 void FusedSra::launch(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream,
                       bool oneshot) {
   if (!heap_->connected()) throw std::runtime_error("cgx: symmetric heap is not connected");
-  if (dp.plan.blocks.empty()) return;
+  if (dp.plan.items.empty()) return;
   ++epoch_;
   SraParams p;
+  std::memset(&p, 0, sizeof(p));
   p.data = data;
-  p.blocks = dp.d_blocks;
-  p.lane_first = dp.d_lane_first;
+  p.items = dp.d_items;
+  p.item_first = dp.d_item_first;
   p.rank = rank();
   p.world = world();
   p.lanes = dp.plan.lanes;
   p.dtype = dp.plan.dtype;
-  p.epoch = epoch_;
+  p.epoch_hint = epoch_;
   p.prescale = prescale;
   p.rng = make_rng_key(rng, rank(), 0);
-  // one-shot calls alternate between two dedicated regions: a peer can be at most one call ahead
-  const int parity = oneshot ? (int)(oneshot_calls_++ & 1u) : 0;
   p.slot_bytes = oneshot ? heap_->layout().os_slot_bytes : heap_->layout().slot_bytes;
   p.flag_stride = heap_->layout().flag_stride;
+  p.os_parity_stride = (uint32_t)(heap_->layout().os_off[1] - heap_->layout().os_off[0]);
   for (int q = 0; q < kMaxPeers; ++q) {
     const bool valid = q < world();
-    p.recv1[q] = valid ? (oneshot ? heap_->oneshot(q, parity) : heap_->recv1(q)) : nullptr;
+    // one-shot: recv1 is region 0 of the alternating pair; the kernel adds the parity offset
+    p.recv1[q] = valid ? (oneshot ? heap_->oneshot(q, 0) : heap_->recv1(q)) : nullptr;
     p.recv2[q] = valid ? heap_->recv2(q) : nullptr;
     p.flags1[q] = valid ? heap_->flags1(q) : nullptr;
     p.flags2[q] = valid ? heap_->flags2(q) : nullptr;
   }
+  const bool mc = use_mc_ && dp.multicast_ok;
+  p.mc_recv1 = (mc && oneshot) ? heap_->mc_oneshot(0) : nullptr;
+  p.mc_recv2 = (mc && !oneshot) ? heap_->mc_recv2() : nullptr;
+  p.mc_reduce = (mc && !oneshot && use_mc_reduce_) ? 1 : 0;
   p.status = heap_->status_device();
   p.timeout_ns = timeout_ns_;
+  p.sync = heap_->sync_device();
   p.trace = nullptr;
   if (trace_on_ && d_trace_) {
     // slot 0 takes a minimum, the rest maxima: 0xFF.. / 0 initialisation per lane
@@ -154,22 +161,28 @@ void FusedSra::launch(const DevicePlan& dp, void* data, float prescale, const Rn
     p.trace = d_trace_;
   }
   last_lanes_ = dp.plan.lanes;
-  p.variant = oneshot ? 3 : variant_;
-  p.uniform_bits = dp.uniform_bits;
+  p.uniform_bits = dp.plan.uniform_bits;
+  p.slice_elems = (int)dp.plan.slice_elems;
+  p.oneshot = oneshot ? 1 : 0;
   cuda_check(launch_sra_fused(p, stream), "launch_sra_fused");
   ++launches_;
 }
 
-void FusedSra::check_status() {
-  uint32_t s = heap_->status_host();
-  if (s == 0) return;
-  heap_->clear_status();
+std::string FusedSra::status_message() const {
+  const uint32_t s = heap_->status_host();
+  if (s == 0) return std::string();
   const uint32_t code = s & 0xFF, peer = (s >> 8) & 0xFF, lane = s >> 16;
-  throw std::runtime_error("cgx: fused allreduce kernel timed out on rank " + std::to_string(rank()) +
-                           " waiting for rank " + std::to_string(peer) + " (phase " + std::to_string(code) +
-                           ", lane " + std::to_string(lane) +
-                           "); a peer died, is stuck, or issued collectives in a different order "
-                           "(raise CGX_TIMEOUT_MS if the job is just slow)");
+  return "cgx: fused allreduce kernel timed out on rank " + std::to_string(rank()) + " waiting for rank " +
+         std::to_string(peer) + " (phase " + std::to_string(code) + ", lane " + std::to_string(lane) +
+         "); a peer died, is stuck, or issued collectives in a different order "
+         "(raise CGX_TIMEOUT_MS if the job is just slow)";
+}
+
+void FusedSra::check_status() {
+  const std::string msg = status_message();
+  if (msg.empty()) return;
+  heap_->clear_status();
+  throw std::runtime_error(msg);
 }
 
 }  // namespace cgx

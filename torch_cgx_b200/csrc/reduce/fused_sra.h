@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <memory>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -19,9 +20,9 @@ namespace cgx {
 
 struct DevicePlan {
   Plan plan;
-  BlockDesc* d_blocks = nullptr;
-  uint32_t* d_lane_first = nullptr;
-  int uniform_bits = 0;  // bits shared by every compressed block, or 0
+  WarpItem* d_items = nullptr;       // flattened warp work list (device)
+  uint32_t* d_item_first = nullptr;  // [world * lanes + 1]
+  bool multicast_ok = false;         // every compressed item has a width multimem.st can carry (2/4/8)
 };
 
 class FusedSra {
@@ -35,8 +36,10 @@ class FusedSra {
 
   // Build (or fetch) the plan for `layers`; returns nullptr if its largest
   // chunk does not fit the heap's slots (caller must split the call).
+  //  max_lanes > 0 caps the number of lanes (CTAs) below the group's maximum: calls that overlap
+  //  with compute (DDP buckets during backward) leave most SMs to the model.
   const DevicePlan* prepare(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
-                            cudaStream_t stream);
+                            cudaStream_t stream, int max_lanes = 0);
 
   // In-place allreduce of `data` over the layers of `dp`. Stream-ordered, no
   // host synchronisation. Every rank must call this the same number of times
@@ -46,11 +49,14 @@ class FusedSra {
   // One-shot variant (single signalling hop, for latency-bound messages): plan over the WHOLE
   // buffer (one chunk); nullptr if its packed image does not fit the heap's one-shot slots.
   const DevicePlan* prepare_oneshot(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
-                                    cudaStream_t stream);
+                                    cudaStream_t stream, int max_lanes = 0);
   void run_oneshot(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream);
 
   // throws std::runtime_error if a kernel reported a timeout
   void check_status();
+  // same, without throwing: empty string when healthy (does not clear the status)
+  std::string status_message() const;
+  bool uses_multicast() const { return use_mc_; }
 
   // Tracing: when enabled, the next run() records per-lane phase timestamps
   // (device globaltimer, ns); read_trace() synchronises the device and returns
@@ -68,17 +74,17 @@ class FusedSra {
   int max_lanes_;
   uint64_t timeout_ns_;
   uint32_t min_lane_elems_;
-  uint32_t epoch_ = 0;
+  uint32_t epoch_ = 0;  // host mirror of the device-side call counter (DeviceSync)
   uint64_t launches_ = 0;
-  int variant_ = 0;
+  bool use_mc_ = false;      // NVLS stores (multimem.st) for phase B / one-shot
+  bool use_mc_reduce_ = false;  // NVLS in-switch reduction (multimem.ld_reduce) for raw items
   unsigned long long* d_trace_ = nullptr;
   bool trace_on_ = false;
   int last_lanes_ = 0;
-  uint32_t oneshot_calls_ = 0;
   uint64_t generation_ = 1;
   static constexpr size_t kMaxCachedPlans = 1024;
   const DevicePlan* prepare_impl(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete,
-                                 cudaStream_t stream, int plan_world, uint32_t capacity);
+                                 cudaStream_t stream, int plan_world, uint32_t capacity, int max_lanes);
   void launch(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream,
               bool oneshot);
   std::unordered_map<uint64_t, std::unique_ptr<DevicePlan>> cache_;

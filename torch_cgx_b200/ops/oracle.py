@@ -1,6 +1,6 @@
 """Pure-PyTorch reference ("oracle") of the quantization numerics, SURVEY.md §2.7:
 
-    unit_k = (max_k - min_k) / (2^b - 1)
+    unit_k = (max_k - min_k) * fp32(1 / (2^b - 1))
     q_i    = min(floor((x_i - min_k) / unit_k + r), 2^b - 1),  r = 0.5 ; unit_k < 1e-10 => q_i = 0
     x^_i   = min_k + unit_k * q_i
 
@@ -44,7 +44,7 @@ def quantize_dequantize(x: torch.Tensor, bits: int, bucket_size: int) -> Tuple[t
     mn = b.min(dim=1, keepdim=True).values
     mx = b.max(dim=1, keepdim=True).values
     levels = float((1 << bits) - 1)
-    unit = ((mx - mn) / levels).float()
+    unit = ((mx - mn).float() * (torch.tensor(1.0, dtype=torch.float32) / torch.tensor(levels, dtype=torch.float32))).float()
     inv = torch.where(unit < EPS, torch.zeros_like(unit), (1.0 / unit).float())
     t = _fma32((b - mn).float(), inv.expand_as(b), torch.full_like(b, 0.5))
     q = torch.clamp(torch.floor(t), 0, levels)
