@@ -71,60 +71,6 @@ def reference_unavailable():
     print(json.dumps({"impl": "reference", "unavailable": why}))
 
 
-class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index: int):
-        self.index = index
-        self.proc = None
-        self.lines = []
-        self.thread = None
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
-            return
-        def pump():
-            for line in self.proc.stdout:
-                self.lines.append(line.strip())
-        self.thread = threading.Thread(target=pump, daemon=True)
-        self.thread.start()
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
-
-
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -145,6 +91,7 @@ def main():
 
     import torch_cgx_b200 as cgx
     from torch_cgx_b200 import models
+    from torch_cgx_b200.utils.clocks import ClockSampler
     from torch_cgx_b200.utils.data import CudaPrefetcher, SyntheticHostDataset
 
     rank = int(os.environ.get("RANK", "0"))

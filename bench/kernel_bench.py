@@ -1,8 +1,11 @@
 #!/usr/bin/env python
-"""Single-GPU kernel microbenchmarks (device-timed with CUDA events, L2 flushed
-between iterations): standalone quantize / dequantize and the fused kernel in
-world=1 mode (load -> min/max -> quantize -> pack -> self-decode), reported as
-achieved HBM GB/s against MEASURED_PEAKS.json."""
+"""Single-GPU kernel microbenchmarks: the kernels ALONE (pre-planned, pre-allocated), device-timed
+with CUDA events, L2 flushed between iterations, clocks sampled during the run.
+
+  quantize / dequantize   standalone item kernels (_C.PreparedCodec)
+  fused_w1                the fused SRA kernel in world=1 mode (load -> min/max -> quantize -> pack
+                          -> self-decode): what phase B does per element, minus the peers
+reported as achieved HBM GB/s (algorithmic bytes / time) against MEASURED_PEAKS.json."""
 from __future__ import annotations
 
 import argparse
@@ -16,6 +19,7 @@ sys.path.insert(0, str(ROOT))
 import torch  # noqa: E402
 
 import torch_cgx_b200 as cgx  # noqa: E402
+from torch_cgx_b200.utils.clocks import ClockSampler  # noqa: E402
 
 C = cgx._C
 
@@ -34,15 +38,17 @@ def time_op(fn, flush, iters=10, warmup=3):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ts.sort()
-    return ts[len(ts) // 2]
+    return ts[len(ts) // 2], ts[0]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/kernel_bench.json")
     ap.add_argument("--sizes-mb", default="1,8,25,64,256")
-    ap.add_argument("--lanes", type=int, default=148)
+    ap.add_argument("--lanes", type=int, default=296)
     ap.add_argument("--bits", default="2,4,8")
+    ap.add_argument("--buckets", default="512")
+    ap.add_argument("--dtypes", default="float32,bfloat16")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     peaks = {}
@@ -52,31 +58,46 @@ def main():
     hbm = peaks.get("hbm_gbs", 6650.0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rows = []
+    sampler = ClockSampler(0).start()
     for mb in [int(x) for x in args.sizes_mb.split(",")]:
-        for dtype in (torch.float32, torch.bfloat16):
-            for bits in [int(b) for b in args.bits.split(",")]:
-                n = (mb << 20) // (4 if dtype == torch.float32 else 2)
-                x = torch.randn(n, device=dev).to(dtype)
-                layers = [(0, n, bits, 512)]
-                es = x.element_size()
-                w = C.quantize(x, layers, 1, 1, False, 1.0, False, 0, 0, 0, 0, 2048)
-                wire = cgx.ops.wire_bytes(n, bits, 512, es)
-                tq = time_op(lambda: C.quantize(x, layers, 1, 1, False, 1.0, False, 0, 0, 0, 0, 2048), flush)
-                td = time_op(lambda: C.dequantize(w, x, layers, 1, 1, False, 2048), flush)
-                g = C.LocalSraGroup(1, args.lanes, max(64 << 20, n * es + (1 << 20)), 5000, 2048)
-                y = x.clone()
-                tf = time_op(lambda: g.allreduce([y], layers), flush)
-                row = {
-                    "mb": mb, "dtype": str(dtype).split(".")[-1], "bits": bits,
-                    "quantize_ms": round(tq, 4), "quantize_gbs": round((n * es + wire) / tq / 1e6, 1),
-                    "dequantize_ms": round(td, 4), "dequantize_gbs": round((n * es + wire) / td / 1e6, 1),
-                    "fused_w1_ms": round(tf, 4), "fused_w1_gbs": round((2 * n * es) / tf / 1e6, 1),
-                    "fused_w1_frac_of_measured_hbm": round((2 * n * es) / tf / 1e6 / hbm, 3),
-                }
-                rows.append(row)
-                print(json.dumps(row), flush=True)
+        for dname in args.dtypes.split(","):
+            dtype = getattr(torch, dname)
+            for bucket in [int(b) for b in args.buckets.split(",")]:
+                for bits in [int(b) for b in args.bits.split(",")]:
+                    n = (mb << 20) // (4 if dtype == torch.float32 else 2)
+                    x = torch.randn(n, device=dev).to(dtype)
+                    layers = [(0, n, bits, bucket)]
+                    es = x.element_size()
+                    codec = C.PreparedCodec(layers, dtype, 0, False)
+                    wire = torch.zeros(codec.wire_bytes(), dtype=torch.uint8, device=dev)
+                    out = torch.empty_like(x)
+                    wb = cgx.ops.wire_bytes(n, bits, bucket, es)
+                    tq, tq_min = time_op(lambda: codec.quantize(x, wire), flush)
+                    td, td_min = time_op(lambda: codec.dequantize(wire, out), flush)
+                    g = C.LocalSraGroup(1, args.lanes, max(64 << 20, n * es + (1 << 20)), 5000, 4096)
+                    y = x.clone()
+                    g.allreduce([y], layers)  # plan + upload outside the timed region
+                    tf, tf_min = time_op(lambda: g.allreduce([y], layers), flush)
+                    row = {
+                        "mb": mb, "dtype": dname, "bits": bits, "bucket": bucket,
+                        "quantize_us": round(tq * 1e3, 1), "quantize_gbs": round((n * es + wb) / tq / 1e6, 1),
+                        "quantize_frac_of_measured_hbm": round((n * es + wb) / tq / 1e6 / hbm, 3),
+                        "dequantize_us": round(td * 1e3, 1), "dequantize_gbs": round((n * es + wb) / td / 1e6, 1),
+                        "dequantize_frac_of_measured_hbm": round((n * es + wb) / td / 1e6 / hbm, 3),
+                        "fused_w1_us": round(tf * 1e3, 1), "fused_w1_min_us": round(tf_min * 1e3, 1),
+                        "fused_w1_gbs": round((2 * n * es) / tf / 1e6, 1),
+                        "fused_w1_frac_of_measured_hbm": round((2 * n * es) / tf / 1e6 / hbm, 3),
+                    }
+                    rows.append(row)
+                    print(json.dumps(row), flush=True)
+                    del g, codec
+    clocks = sampler.stop()
     Path(args.out).parent.mkdir(parents=True, exist_ok=True)
-    Path(args.out).write_text(json.dumps({"hbm_gbs_measured": hbm, "note": "quantize/dequantize timings include the op's own output allocation (torch empty/zeros)", "rows": rows}, indent=1))
+    Path(args.out).write_text(json.dumps({
+        "hbm_gbs_measured": hbm, "clocks": clocks,
+        "timing": "CUDA events around ONE launch, median of 10 after 3 warm-ups, 256 MB L2 flush before every timed launch",
+        "rows": rows}, indent=1))
+    print(json.dumps({"clocks": clocks}))
 
 
 if __name__ == "__main__":

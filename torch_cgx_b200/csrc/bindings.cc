@@ -223,6 +223,63 @@ at::Tensor py_dequantize(const at::Tensor& wire, const at::Tensor& like, const s
   return out;
 }
 
+// ---- pre-planned codec: the kernels alone, no per-call planning or allocation ----------------
+// (kernel microbenchmarks, and users who quantize the same layout repeatedly)
+class PreparedCodec {
+ public:
+  PreparedCodec(const std::vector<LayerTuple>& layers, at::ScalarType dtype, int64_t device, bool skip_incomplete) {
+    at::Tensor probe = at::empty({0}, at::TensorOptions().dtype(dtype));
+    dt_ = cgx_dtype(probe);
+    plan_ = build_plan(to_layers(layers), make_opts(1, 1, dt_, skip_incomplete, 1 << 30));
+    c10::cuda::CUDAGuard g((c10::DeviceIndex)device);
+    items_ = at::empty({(int64_t)(plan_.items.size() * sizeof(WarpItem) + 16)},
+                       at::TensorOptions().dtype(at::kByte).device(at::kCUDA, device));
+    cuda_check(cudaMemcpy(items_.data_ptr(), plan_.items.data(), plan_.items.size() * sizeof(WarpItem),
+                          cudaMemcpyHostToDevice),
+               "upload items");
+  }
+  int64_t wire_bytes() const { return (int64_t)wire_row_bytes(plan_); }
+  int64_t numel() const { return (int64_t)plan_.numel; }
+  int64_t num_items() const { return (int64_t)plan_.items.size(); }
+  void quantize(const at::Tensor& x, at::Tensor& wire, double prescale, bool stochastic, uint64_t seed, uint32_t seq) {
+    check(x, wire);
+    c10::cuda::CUDAGuard g(x.device());
+    cuda_check(launch_quantize_items(args(), x.data_ptr(), wire.data_ptr<uint8_t>(), (float)prescale,
+                                     make_rng_key(make_rng(stochastic, seed, seq), 0, 0),
+                                     c10::cuda::getCurrentCUDAStream()),
+               "quantize_items");
+  }
+  void dequantize(const at::Tensor& wire, at::Tensor& out) {
+    check(out, wire);
+    c10::cuda::CUDAGuard g(out.device());
+    cuda_check(launch_dequantize_items(args(), wire.data_ptr<uint8_t>(), out.data_ptr(),
+                                       c10::cuda::getCurrentCUDAStream()),
+               "dequantize_items");
+  }
+
+ private:
+  void check(const at::Tensor& x, const at::Tensor& wire) const {
+    TORCH_CHECK(x.is_cuda() && x.is_contiguous() && cgx_dtype(x) == dt_ && (uint64_t)x.numel() == plan_.numel,
+                "PreparedCodec: tensor does not match the prepared layout");
+    TORCH_CHECK(wire.is_cuda() && wire.is_contiguous() && wire.scalar_type() == at::kByte &&
+                    (size_t)wire.numel() >= wire_row_bytes(plan_),
+                "PreparedCodec: wire buffer too small");
+  }
+  ItemKernelArgs args() const {
+    ItemKernelArgs a;
+    a.items = (const WarpItem*)items_.data_ptr();
+    a.first = 0;
+    a.count = (uint32_t)plan_.items.size();
+    a.dtype = dt_;
+    a.slice_elems = (int)plan_.slice_elems;
+    a.uniform_bits = plan_.uniform_bits;
+    return a;
+  }
+  Plan plan_;
+  int dt_ = kF32;
+  at::Tensor items_;
+};
+
 // ---- single-process multi-rank harness --------------------------------------
 class LocalSraGroup {
  public:
@@ -470,6 +527,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("max_resident_ctas", [](int dtype) { return sra_max_resident_ctas(dtype); }, py::arg("dtype") = 0);
 
+  py::class_<PreparedCodec>(m, "PreparedCodec")
+      .def(py::init<const std::vector<LayerTuple>&, at::ScalarType, int64_t, bool>(), py::arg("layers"),
+           py::arg("dtype"), py::arg("device") = 0, py::arg("skip_incomplete") = false)
+      .def("wire_bytes", &PreparedCodec::wire_bytes)
+      .def("numel", &PreparedCodec::numel)
+      .def("num_items", &PreparedCodec::num_items)
+      .def("quantize", &PreparedCodec::quantize, py::arg("x"), py::arg("wire"), py::arg("prescale") = 1.0,
+           py::arg("stochastic") = false, py::arg("seed") = 0, py::arg("seq") = 0)
+      .def("dequantize", &PreparedCodec::dequantize, py::arg("wire"), py::arg("out"));
   py::class_<LocalSraGroup>(m, "LocalSraGroup")
       .def(py::init<int, int, int64_t, int64_t, int64_t>(), py::arg("world"), py::arg("lanes"),
            py::arg("slot_bytes"), py::arg("timeout_ms") = 5000, py::arg("min_lane_elems") = 2048)

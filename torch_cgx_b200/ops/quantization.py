@@ -65,7 +65,9 @@ def wire_bytes(numel: int, bits: int, bucket_size: int, elsize: int = 4) -> int:
     if bits >= 32:
         return numel * elsize
     nb = (numel + bucket_size - 1) // bucket_size
-    return nb * 8 + ((numel + 7) // 8) * bits
+    # every bucket starts a fresh pack group of 8 values (wire.h: block_num_groups)
+    groups = (numel // bucket_size) * ((bucket_size + 7) // 8) + ((numel % bucket_size) + 7) // 8
+    return nb * 8 + groups * bits
 
 
 def compression_ratio(numel: int, bits: int, bucket_size: int, elsize: int = 4) -> float:
