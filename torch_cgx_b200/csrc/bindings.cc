@@ -316,15 +316,19 @@ class LocalSraGroup {
     ready.record(cur);
     const RngParams rng = make_rng(stochastic, seed, seq);
     std::vector<const DevicePlan*> plans(world_);
+    bool fresh_plan = false;
     for (int r = 0; r < world_; ++r) {
       TORCH_CHECK(tensors[r].is_cuda() && tensors[r].is_contiguous() && cgx_dtype(tensors[r]) == dt, "bad tensor");
       ready.block(streams_[r]);
+      const size_t before = fused_[r]->num_plans();
       plans[r] = oneshot ? fused_[r]->prepare_oneshot(specs, dt, skip_incomplete, streams_[r].stream())
                          : fused_[r]->prepare(specs, dt, skip_incomplete, streams_[r].stream());
       TORCH_CHECK(plans[r] != nullptr, "plan does not fit the heap slots (raise slot_bytes)");
+      fresh_plan = fresh_plan || fused_[r]->num_plans() != before;
     }
     // make sure every plan upload has landed before any virtual rank starts spinning
-    for (int r = 0; r < world_; ++r) streams_[r].synchronize();
+    if (fresh_plan)
+      for (int r = 0; r < world_; ++r) streams_[r].synchronize();
     for (int r = 0; r < world_; ++r) {
       const float ps = average ? 1.0f / (float)world_ : 1.0f;
       if (oneshot)

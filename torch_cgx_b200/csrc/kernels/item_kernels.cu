@@ -17,28 +17,43 @@ constexpr int kWarps = kThreads / 32;
 __device__ __forceinline__ uint32_t global_warp() { return blockIdx.x * kWarps + (threadIdx.x >> 5); }
 __device__ __forceinline__ uint32_t total_warps() { return gridDim.x * kWarps; }
 
+// Each warp walks items first+w, first+w+stride, ...; the descriptor of the NEXT item is loaded
+// before the current one is processed so that its latency hides behind the work.
+#define CGX_ITEM_LOOP(it)                                                       \
+  const uint32_t stride_ = total_warps();                                       \
+  uint32_t i_ = global_warp();                                                  \
+  WarpItem it, next_;                                                           \
+  if (i_ < count) it = items[first + i_];                                       \
+  for (; i_ < count; i_ += stride_, it = next_)                                 \
+    if (next_ = (i_ + stride_ < count) ? items[first + i_ + stride_] : it, true)
+
 // wire = quantize(src * prescale); TS = T (tensor) or float (fp32 scratch indexed from base_elem);
 // out != nullptr: also write the self-decoded values (T, indexed from the tensor base)
 template <typename TS, typename T, int KB, int GPL>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 quantize_items_kernel(const TS* __restrict__ src, uint32_t base_elem, const WarpItem* __restrict__ items,
                       uint32_t first, uint32_t count, uint8_t* wire, float prescale, const RngKey rng,
                       T* __restrict__ out) {
-  __shared__ uint8_t* s_base[1];
-  if (threadIdx.x == 0) s_base[0] = wire;
-  __syncthreads();
-  const DstSet ds{s_base, nullptr, 0u, 1, -1, nullptr};
+  const OneDst ds{wire};
   const SrcSet no_src{nullptr, 0u, 0, -1};
-  for (uint32_t i = global_warp(); i < count; i += total_warps()) {
-    const WarpItem it = items[first + i];
+  CGX_ITEM_LOOP(it) {
     const uint32_t kind = item_kind(it);
     const TS* s = src + (it.elem_off - base_elem);
     T* o = out ? out + it.elem_off : nullptr;
     if (kind == kItemFull) {
-      if (out)
-        full_send<TS, T, KB, GPL, true>(s, it, prescale, rng, ds, o);
-      else
-        full_send<TS, T, KB, GPL, false>(s, it, prescale, rng, ds, o);
+      const bool al = group_aligned<TS>(s) && (o == nullptr || group_aligned<T>(o));
+      if (al) {
+        float x[GPL][8];
+        slice_load_vec<TS, GPL>(s, x);
+        if (o)
+          full_send_x<T, KB, GPL, true, true>(x, it, prescale, rng, ds, o);
+        else
+          full_send_x<T, KB, GPL, false, true>(x, it, prescale, rng, ds, o);
+      } else if (o) {
+        full_send_unaligned<TS, T, KB, GPL, true>(s, it, prescale, rng, ds, o);
+      } else {
+        full_send_unaligned<TS, T, KB, GPL, false>(s, it, prescale, rng, ds, o);
+      }
     } else if (kind == kItemBucket) {
       bucket_quantize<TS, T>(s, it, prescale, rng, no_src, ds, o);
     } else {
@@ -55,16 +70,21 @@ quantize_items_kernel(const TS* __restrict__ src, uint32_t base_elem, const Warp
 }
 
 template <typename T, int KB, int GPL>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 dequantize_items_kernel(const uint8_t* __restrict__ wire, const WarpItem* __restrict__ items, uint32_t first,
                         uint32_t count, T* __restrict__ dst) {
   const SrcSet ss{wire, 0u, 1, -1};
-  for (uint32_t i = global_warp(); i < count; i += total_warps()) {
-    const WarpItem it = items[first + i];
+  CGX_ITEM_LOOP(it) {
     const uint32_t kind = item_kind(it);
     T* o = dst + it.elem_off;
     if (kind == kItemFull) {
-      full_recv<T, KB, GPL>(ss, it, o);
+      if (group_aligned<T>(o)) {
+        SliceWords<GPL> w;
+        slice_fetch<KB, GPL>(wire, it.meta_off, it.pay_off, item_lpb_log2(it), KB ? KB : item_bits(it), w);
+        full_recv_w<T, KB, GPL, true>(w, it, o);
+      } else {
+        full_recv_unaligned<T, KB, GPL>(ss, it, o);
+      }
     } else if (kind == kItemBucket) {
       bucket_recv<T>(ss, it, o);
     } else {
@@ -78,29 +98,38 @@ dequantize_items_kernel(const uint8_t* __restrict__ wire, const WarpItem* __rest
 // acc (fp32 scratch) = float(init_src) * prescale   (init_src != nullptr)
 // acc += decode(wire)                                (wire != nullptr)
 template <typename T, int KB, int GPL>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 accumulate_items_kernel(const uint8_t* __restrict__ wire, const WarpItem* __restrict__ items, uint32_t first,
                         uint32_t count, float* __restrict__ acc, uint32_t base_elem, const T* __restrict__ init_src,
                         float prescale) {
-  for (uint32_t i = global_warp(); i < count; i += total_warps()) {
-    const WarpItem it = items[first + i];
+  CGX_ITEM_LOOP(it) {
     const uint32_t kind = item_kind(it);
     float* a = acc + (it.elem_off - base_elem);
     if (kind == kItemFull) {
       const int bits = KB ? KB : item_bits(it);
       const uint32_t lg = item_lpb_log2(it);
       float x[GPL][8];
-      if (init_src)
-        slice_load<T, GPL>(init_src + it.elem_off, prescale, x);
-      else
-        slice_load<float, GPL>(a, 1.0f, x);
-      if (wire) {
-        uint32_t lo[GPL], hi[GPL];
-        BucketMeta pm[GPL];
-        slice_fetch<KB, GPL>(wire, it.meta_off, it.pay_off, lg, bits, lo, hi, pm);
-        slice_decode<KB, GPL, true>(lo, hi, pm, bits, x);
+      if (init_src) {
+        const T* s = init_src + it.elem_off;
+        if (group_aligned<T>(s))
+          slice_load_vec<T, GPL>(s, x);
+        else
+          slice_load_scalar<T, GPL>(s, x);
+        slice_scale<GPL>(x, prescale);
+      } else if (group_aligned<float>(a)) {
+        slice_load_vec<float, GPL>(a, x);
+      } else {
+        slice_load_scalar<float, GPL>(a, x);
       }
-      slice_store<float, GPL>(a, x);
+      if (wire) {
+        SliceWords<GPL> w;
+        slice_fetch<KB, GPL>(wire, it.meta_off, it.pay_off, lg, bits, w);
+        slice_decode<KB, GPL, true>(w, bits, x);
+      }
+      if (group_aligned<float>(a))
+        slice_store<float, GPL, true>(a, x);
+      else
+        slice_store<float, GPL, false>(a, x);
     } else if (kind == kItemBucket) {
       const uint32_t n = item_n(it);
       const int bits = item_bits(it);
@@ -156,7 +185,7 @@ int grid_for(uint32_t count) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const uint32_t want = (count + kWarps - 1) / kWarps;
-  const uint32_t cap = (uint32_t)sms * 8u;
+  const uint32_t cap = (uint32_t)sms * 3u;  // one resident wave (3 CTAs of 8 warps per SM); warps loop
   return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 int grid_for_elems(uint64_t n) {

@@ -1,9 +1,10 @@
 // Item-level operations built from item_path.cuh. Each function is executed by ONE warp on ONE
-// item; the hot (full-slice) versions are force-inlined templates, the cold (generic bucket,
-// raw tail) versions are deliberately out of line so that the hot loops stay a few hundred
-// instructions long.
+// item. The hot versions work on a slice whose values are already in registers (the callers
+// prefetch the next item's data while the current one is processed) and assume 16/32 B aligned
+// gradients; everything rare -- unaligned slices, generic buckets, raw tails -- is deliberately
+// out of line so that the hot loops stay a few hundred instructions long.
 //
-//   *_send     quantize my values of an item and store the packed words to a destination set
+//   *_send     quantize my values of an item and store the packed words to a destination
 //              (SRA phase A, one-shot phase 1, standalone quantize)
 //   *_reduce   own values + the decoded copies of W-1 sources, requantize, publish, self-decode
 //              (SRA phase B)
@@ -22,20 +23,39 @@ template <int GPL>
 struct SliceCfg {
   static constexpr uint32_t kElems = 256u * GPL;
   static constexpr uint32_t kLgAll = GPL == 4 ? 7u : 6u;  // log2(bucket/8) of a bucket spanning the slice
-  static constexpr int kPeerBatch = GPL == 4 ? 2 : 4;     // sources fetched before any is consumed
+  static constexpr int kPeerBatch = 2;  // sources fetched before any is consumed
 };
 
+// one bucket == the whole slice (512 / 1024-element buckets): the common case
+template <int GPL>
+__device__ __forceinline__ bool slice_single_bucket(uint32_t lg) {
+  return GPL == 4 || lg == SliceCfg<GPL>::kLgAll;
+}
+
 // ---- slice <-> registers -------------------------------------------------------------
+// issue the (vector) loads of a slice: lane l gets groups l, l+32, ...; `src` must be group aligned
 template <typename TS, int GPL>
-__device__ __forceinline__ void slice_load(const TS* __restrict__ src, float prescale, float (&x)[GPL][8]) {
+__device__ __forceinline__ void slice_load_vec(const TS* __restrict__ src, float (&x)[GPL][8]) {
   const TS* p = src + lane_id() * 8u;
-  if (group_aligned<TS>(src)) {
 #pragma unroll
-    for (int k = 0; k < GPL; ++k) load8_vec<TS>(p + k * 256, x[k]);
-  } else {
+  for (int k = 0; k < GPL; ++k) load8_vec<TS>(p + k * 256, x[k]);
+}
+template <typename TS, int GPL>
+__device__ __forceinline__ void slice_load_scalar(const TS* __restrict__ src, float (&x)[GPL][8]) {
+  const TS* p = src + lane_id() * 8u;
 #pragma unroll
-    for (int k = 0; k < GPL; ++k) load8_scalar<TS>(p + k * 256, 8, x[k]);
-  }
+  for (int k = 0; k < GPL; ++k) load8_scalar<TS>(p + k * 256, 8, x[k]);
+}
+// pull the slice towards L2 without occupying registers (phase B prefetches its next item this way:
+// its registers are taken by the peers' words)
+template <typename TS, int GPL>
+__device__ __forceinline__ void slice_prefetch_l2(const TS* __restrict__ src) {
+  const TS* p = src + lane_id() * 8u;
+#pragma unroll
+  for (int k = 0; k < GPL; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + k * 256));
+}
+template <int GPL>
+__device__ __forceinline__ void slice_scale(float (&x)[GPL][8], float prescale) {
   if (prescale != 1.0f) {
 #pragma unroll
     for (int k = 0; k < GPL; ++k)
@@ -43,16 +63,15 @@ __device__ __forceinline__ void slice_load(const TS* __restrict__ src, float pre
       for (int j = 0; j < 8; ++j) x[k][j] = __fmul_rn(x[k][j], prescale);
   }
 }
-
-template <typename TO, int GPL>
+template <typename TO, int GPL, bool VEC>
 __device__ __forceinline__ void slice_store(TO* __restrict__ dst, const float (&x)[GPL][8]) {
   TO* p = dst + lane_id() * 8u;
-  if (group_aligned<TO>(dst)) {
 #pragma unroll
-    for (int k = 0; k < GPL; ++k) store8_vec<TO>(p + k * 256, x[k]);
-  } else {
-#pragma unroll
-    for (int k = 0; k < GPL; ++k) store8_scalar<TO>(p + k * 256, 8, x[k]);
+  for (int k = 0; k < GPL; ++k) {
+    if (VEC)
+      store8_vec<TO>(p + k * 256, x[k]);
+    else
+      store8_scalar<TO>(p + k * 256, 8, x[k]);
   }
 }
 
@@ -67,7 +86,7 @@ __device__ __forceinline__ void slice_meta(const float (&x)[GPL][8], uint32_t lg
     mx[k] = CGX_INF_NEG;
     minmax8(x[k], mn[k], mx[k]);
   }
-  if (GPL == 4 || lg == SliceCfg<GPL>::kLgAll) {  // one bucket == the slice (512 / 1024): the common case
+  if (slice_single_bucket<GPL>(lg)) {
     float a = mn[0], b = mx[0];
 #pragma unroll
     for (int k = 1; k < GPL; ++k) {
@@ -95,10 +114,10 @@ __device__ __forceinline__ void slice_meta(const float (&x)[GPL][8], uint32_t lg
   }
 }
 
-template <int GPL>
-__device__ __forceinline__ void slice_store_meta(const BucketMeta (&m)[GPL], uint32_t lg, const DstSet& ds,
+template <int GPL, typename DST>
+__device__ __forceinline__ void slice_store_meta(const BucketMeta (&m)[GPL], uint32_t lg, const DST& ds,
                                                  uint32_t meta_off) {
-  if (GPL == 4 || lg == SliceCfg<GPL>::kLgAll) {
+  if (slice_single_bucket<GPL>(lg)) {
     if (lane_id() == 0) dst_st_v2(ds, meta_off, __float_as_uint(m[0].unit), __float_as_uint(m[0].min));
   } else {
 #pragma unroll
@@ -111,34 +130,26 @@ __device__ __forceinline__ void slice_store_meta(const BucketMeta (&m)[GPL], uin
 }
 
 // quantize + pack + store the slice; SELF: also write the decoded values (what every receiver
-// will decode from the same bytes) to `self_out`
-template <typename TO, int KB, int GPL, bool SELF, bool STOCH>
-__device__ __forceinline__ void slice_encode(const float (&x)[GPL][8], const BucketMeta (&m)[GPL],
-                                             const float (&inv)[GPL], int bits, const RngKey& rng,
-                                             uint32_t first_elem, const DstSet& ds, uint32_t pay_off,
-                                             TO* __restrict__ self_out) {
+// will decode from the same bytes) to `self_out` (VEC: it is group aligned).
+// MODE 0: deterministic rounding, every bucket finite (no clamp needed)  1: deterministic  2: stochastic
+template <typename TO, int KB, int GPL, bool SELF, bool VEC, int MODE, typename DST>
+__device__ __forceinline__ void slice_encode_mode(const float (&x)[GPL][8], const BucketMeta (&m)[GPL],
+                                                  const float (&inv)[GPL], int bits, const RngKey& rng,
+                                                  uint32_t first_elem, const DST& ds, uint32_t pay_off,
+                                                  TO* __restrict__ self_out) {
   const float maxlvl = (float)max_level(bits);
-  const bool self_vec = SELF && group_aligned<TO>(self_out);
-  // every bucket of the slice has finite min/max (unit finite <=> max - min finite) -> no clamp
-  bool finite = true;
-#pragma unroll
-  for (int k = 0; k < GPL; ++k) finite = finite && (fabsf(m[k].unit) < CGX_INF_POS);
-  finite = __all_sync(kAll, finite);
 #pragma unroll
   for (int k = 0; k < GPL; ++k) {
     const uint32_t gi = (uint32_t)k * 32u + lane_id();
     float u[8];
-    if (STOCH) {
+    if (MODE == 2) {
       float r[8];
       rounding8(rng, first_elem + gi * 8u, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) u[j] = level_magic<true>(x[k][j], m[k].min, inv[k], r[j], maxlvl);
-    } else if (finite) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) u[j] = level_magic<false>(x[k][j], m[k].min, inv[k], 0.5f, maxlvl);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) u[j] = level_magic<true>(x[k][j], m[k].min, inv[k], 0.5f, maxlvl);
+      for (int j = 0; j < 8; ++j) u[j] = level_magic<MODE == 1>(x[k][j], m[k].min, inv[k], 0.5f, maxlvl);
     }
     uint32_t lo, hi;
     pack_magic<KB>(u, bits, lo, hi);
@@ -147,7 +158,7 @@ __device__ __forceinline__ void slice_encode(const float (&x)[GPL][8], const Buc
       float dec[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) dec[j] = __fmaf_rn(m[k].unit, __fsub_rn(u[j], CGX_MAGIC), m[k].min);
-      if (self_vec)
+      if (VEC)
         store8_vec<TO>(self_out + gi * 8u, dec);
       else
         store8_scalar<TO>(self_out + gi * 8u, 8, dec);
@@ -155,41 +166,65 @@ __device__ __forceinline__ void slice_encode(const float (&x)[GPL][8], const Buc
   }
 }
 
+template <typename TO, int KB, int GPL, bool SELF, bool VEC, typename DST>
+__device__ __forceinline__ void slice_encode(const float (&x)[GPL][8], const BucketMeta (&m)[GPL],
+                                             const float (&inv)[GPL], int bits, const RngKey& rng,
+                                             uint32_t first_elem, const DST& ds, uint32_t pay_off,
+                                             TO* __restrict__ self_out) {
+  if (rng.enabled) {
+    slice_encode_mode<TO, KB, GPL, SELF, VEC, 2>(x, m, inv, bits, rng, first_elem, ds, pay_off, self_out);
+    return;
+  }
+  // every bucket of the slice has finite min/max (unit finite <=> max - min finite) -> no clamp
+  bool finite = true;
+#pragma unroll
+  for (int k = 0; k < GPL; ++k) finite = finite && (fabsf(m[k].unit) < CGX_INF_POS);
+  if (__all_sync(kAll, finite))
+    slice_encode_mode<TO, KB, GPL, SELF, VEC, 0>(x, m, inv, bits, rng, first_elem, ds, pay_off, self_out);
+  else
+    slice_encode_mode<TO, KB, GPL, SELF, VEC, 1>(x, m, inv, bits, rng, first_elem, ds, pay_off, self_out);
+}
+
+// packed words + meta of one source for a slice, as loaded (not yet decoded)
+template <int GPL>
+struct SliceWords {
+  uint32_t lo[GPL], hi[GPL];
+  BucketMeta pm[GPL];
+};
+
 // issue the loads of one source's packed words + meta for the slice (no use yet)
 template <int KB, int GPL>
 __device__ __forceinline__ void slice_fetch(const uint8_t* rec, uint32_t meta_off, uint32_t pay_off, uint32_t lg,
-                                            int bits, uint32_t (&lo)[GPL], uint32_t (&hi)[GPL],
-                                            BucketMeta (&pm)[GPL]) {
+                                            int bits, SliceWords<GPL>& w) {
 #pragma unroll
-  for (int k = 0; k < GPL; ++k) load_word<KB>(rec + pay_off, (uint32_t)k * 32u + lane_id(), bits, lo[k], hi[k]);
-  if (GPL == 4 || lg == SliceCfg<GPL>::kLgAll) {
+  for (int k = 0; k < GPL; ++k) load_word<KB>(rec + pay_off, (uint32_t)k * 32u + lane_id(), bits, w.lo[k], w.hi[k]);
+  if (slice_single_bucket<GPL>(lg)) {
     const uint2 v = ld_sys_v2(rec + meta_off);
 #pragma unroll
     for (int k = 0; k < GPL; ++k) {
-      pm[k].unit = __uint_as_float(v.x);
-      pm[k].min = __uint_as_float(v.y);
+      w.pm[k].unit = __uint_as_float(v.x);
+      w.pm[k].min = __uint_as_float(v.y);
     }
   } else {
 #pragma unroll
     for (int k = 0; k < GPL; ++k) {
       const uint2 v = ld_sys_v2(rec + meta_off + ((((uint32_t)k * 32u + lane_id()) >> lg) * 8u));
-      pm[k].unit = __uint_as_float(v.x);
-      pm[k].min = __uint_as_float(v.y);
+      w.pm[k].unit = __uint_as_float(v.x);
+      w.pm[k].min = __uint_as_float(v.y);
     }
   }
 }
 
 // x (+)= decode(words)
 template <int KB, int GPL, bool ADD>
-__device__ __forceinline__ void slice_decode(const uint32_t (&lo)[GPL], const uint32_t (&hi)[GPL],
-                                             const BucketMeta (&pm)[GPL], int bits, float (&x)[GPL][8]) {
+__device__ __forceinline__ void slice_decode(const SliceWords<GPL>& w, int bits, float (&x)[GPL][8]) {
 #pragma unroll
   for (int k = 0; k < GPL; ++k) {
     float qf[8];
-    unpack_magic<KB>(lo[k], hi[k], bits, qf);
+    unpack_magic<KB>(w.lo[k], w.hi[k], bits, qf);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float d = __fmaf_rn(pm[k].unit, qf[j], pm[k].min);
+      const float d = __fmaf_rn(w.pm[k].unit, qf[j], w.pm[k].min);
       x[k][j] = ADD ? __fadd_rn(x[k][j], d) : d;
     }
   }
@@ -202,81 +237,99 @@ __device__ __forceinline__ void slice_accumulate(const SrcSet& ss, uint32_t meta
   constexpr int kB = SliceCfg<GPL>::kPeerBatch;
   const int cnt = ss.n - (ss.skip >= 0 ? 1 : 0);
   for (int i0 = 0; i0 < cnt; i0 += kB) {
-    uint32_t lo[kB][GPL], hi[kB][GPL];
-    BucketMeta pm[kB][GPL];
+    SliceWords<GPL> w[kB];
 #pragma unroll
     for (int u = 0; u < kB; ++u) {
       const int i = i0 + u;
       if (i < cnt) {
         const int q = (ss.skip >= 0 && i >= ss.skip) ? i + 1 : i;
-        slice_fetch<KB, GPL>(ss.base + (size_t)q * ss.stride, meta_off, pay_off, lg, bits, lo[u], hi[u], pm[u]);
+        slice_fetch<KB, GPL>(ss.base + (size_t)q * ss.stride, meta_off, pay_off, lg, bits, w[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < kB; ++u)
-      if (i0 + u < cnt) slice_decode<KB, GPL, true>(lo[u], hi[u], pm[u], bits, x);
+      if (i0 + u < cnt) slice_decode<KB, GPL, true>(w[u], bits, x);
   }
 }
 
 // ======================================================================================
-// full items
+// full items, values already in registers (x = raw loaded values, not yet prescaled)
 // ======================================================================================
-// TS: element type of the source, TO: element type of the self-decoded output (SELF only)
-template <typename TS, typename TO, int KB, int GPL, bool SELF>
-__device__ __forceinline__ void full_send(const TS* __restrict__ src, const WarpItem& it, float prescale,
-                                          const RngKey& rng, const DstSet& ds, TO* __restrict__ self_out) {
+// TO: element type of the self-decoded output (SELF only)
+template <typename TO, int KB, int GPL, bool SELF, bool VEC, typename DST>
+__device__ __forceinline__ void full_send_x(float (&x)[GPL][8], const WarpItem& it, float prescale, const RngKey& rng,
+                                            const DST& ds, TO* __restrict__ self_out) {
   const int bits = KB ? KB : item_bits(it);
   const uint32_t lg = item_lpb_log2(it);
-  float x[GPL][8];
-  slice_load<TS, GPL>(src, prescale, x);
+  slice_scale<GPL>(x, prescale);
   BucketMeta m[GPL];
   float inv[GPL];
   slice_meta<GPL>(x, lg, bits, m, inv);
   slice_store_meta<GPL>(m, lg, ds, it.meta_off);
-  if (rng.enabled)
-    slice_encode<TO, KB, GPL, SELF, true>(x, m, inv, bits, rng, it.elem_off, ds, it.pay_off, self_out);
-  else
-    slice_encode<TO, KB, GPL, SELF, false>(x, m, inv, bits, rng, it.elem_off, ds, it.pay_off, self_out);
+  slice_encode<TO, KB, GPL, SELF, VEC>(x, m, inv, bits, rng, it.elem_off, ds, it.pay_off, self_out);
 }
 
-template <typename T, int KB, int GPL>
-__device__ __forceinline__ void full_reduce(T* __restrict__ blk, const WarpItem& it, float prescale,
-                                            const RngKey& rng, const SrcSet& ss, const DstSet& ds) {
+template <typename T, int KB, int GPL, bool VEC, typename DST>
+__device__ __forceinline__ void full_reduce_x(float (&x)[GPL][8], T* __restrict__ blk, const WarpItem& it,
+                                              float prescale, const RngKey& rng, const SrcSet& ss, const DST& ds) {
   const int bits = KB ? KB : item_bits(it);
   const uint32_t lg = item_lpb_log2(it);
-  float x[GPL][8];
-  slice_load<T, GPL>(blk, prescale, x);
+  slice_scale<GPL>(x, prescale);
   slice_accumulate<KB, GPL>(ss, it.meta_off, it.pay_off, lg, bits, x);
   BucketMeta m[GPL];
   float inv[GPL];
   slice_meta<GPL>(x, lg, bits, m, inv);
   slice_store_meta<GPL>(m, lg, ds, it.meta_off);
-  if (rng.enabled)
-    slice_encode<T, KB, GPL, true, true>(x, m, inv, bits, rng, it.elem_off, ds, it.pay_off, blk);
-  else
-    slice_encode<T, KB, GPL, true, false>(x, m, inv, bits, rng, it.elem_off, ds, it.pay_off, blk);
+  slice_encode<T, KB, GPL, true, VEC>(x, m, inv, bits, rng, it.elem_off, ds, it.pay_off, blk);
 }
 
-// out = decode(one source)            (ss.n == 1)
-// out = sum of all sources, slot order (one-shot)
-template <typename TO, int KB, int GPL>
-__device__ __forceinline__ void full_recv(const SrcSet& ss, const WarpItem& it, TO* __restrict__ out) {
+// out = decode(already fetched words of ONE source)
+template <typename TO, int KB, int GPL, bool VEC>
+__device__ __forceinline__ void full_recv_w(const SliceWords<GPL>& w, const WarpItem& it, TO* __restrict__ out) {
+  const int bits = KB ? KB : item_bits(it);
+  float x[GPL][8];
+  slice_decode<KB, GPL, false>(w, bits, x);
+  slice_store<TO, GPL, VEC>(out, x);
+}
+
+// out = sum of all sources, slot order (one-shot phase 2)
+template <typename TO, int KB, int GPL, bool VEC>
+__device__ __forceinline__ void full_recv_sum(const SrcSet& ss, const WarpItem& it, TO* __restrict__ out) {
   const int bits = KB ? KB : item_bits(it);
   const uint32_t lg = item_lpb_log2(it);
   float x[GPL][8];
+#pragma unroll
+  for (int k = 0; k < GPL; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[k][j] = 0.f;
+  slice_accumulate<KB, GPL>(ss, it.meta_off, it.pay_off, lg, bits, x);
+  slice_store<TO, GPL, VEC>(out, x);
+}
+
+// ---- the same for slices whose gradients are not vector aligned: out of line, scalar access ----
+template <typename TS, typename TO, int KB, int GPL, bool SELF, typename DST>
+__device__ __noinline__ void full_send_unaligned(const TS* __restrict__ src, const WarpItem it, float prescale,
+                                                 const RngKey rng, const DST ds, TO* __restrict__ self_out) {
+  float x[GPL][8];
+  slice_load_scalar<TS, GPL>(src, x);
+  full_send_x<TO, KB, GPL, SELF, false>(x, it, prescale, rng, ds, self_out);
+}
+template <typename T, int KB, int GPL, typename DST>
+__device__ __noinline__ void full_reduce_unaligned(T* __restrict__ blk, const WarpItem it, float prescale,
+                                                   const RngKey rng, const SrcSet ss, const DST ds) {
+  float x[GPL][8];
+  slice_load_scalar<T, GPL>(blk, x);
+  full_reduce_x<T, KB, GPL, false>(x, blk, it, prescale, rng, ss, ds);
+}
+template <typename TO, int KB, int GPL>
+__device__ __noinline__ void full_recv_unaligned(const SrcSet ss, const WarpItem it, TO* __restrict__ out) {
   if (ss.n == 1) {
-    uint32_t lo[GPL], hi[GPL];
-    BucketMeta pm[GPL];
-    slice_fetch<KB, GPL>(ss.base, it.meta_off, it.pay_off, lg, bits, lo, hi, pm);
-    slice_decode<KB, GPL, false>(lo, hi, pm, bits, x);
+    SliceWords<GPL> w;
+    slice_fetch<KB, GPL>(ss.base, it.meta_off, it.pay_off, item_lpb_log2(it), KB ? KB : item_bits(it), w);
+    full_recv_w<TO, KB, GPL, false>(w, it, out);
   } else {
-#pragma unroll
-    for (int k = 0; k < GPL; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[k][j] = 0.f;
-    slice_accumulate<KB, GPL>(ss, it.meta_off, it.pay_off, lg, bits, x);
+    full_recv_sum<TO, KB, GPL, false>(ss, it, out);
   }
-  slice_store<TO, GPL>(out, x);
 }
 
 // ======================================================================================
@@ -310,9 +363,9 @@ __device__ __forceinline__ void bucket_add_sources(const SrcSet& ss, const WarpI
 
 // phase A / phase B / quantize of a generic bucket. `ss.n == 0`: nothing to add (send);
 // self_out != nullptr: write the self-decoded values there
-template <typename TS, typename TO>
+template <typename TS, typename TO, typename DST>
 __device__ __noinline__ void bucket_quantize(const TS* __restrict__ src, const WarpItem it, float prescale,
-                                             const RngKey rng, const SrcSet ss, const DstSet ds,
+                                             const RngKey rng, const SrcSet ss, const DST ds,
                                              TO* __restrict__ self_out) {
   const uint32_t n = item_n(it);
   const int bits = item_bits(it);
@@ -330,8 +383,7 @@ __device__ __noinline__ void bucket_quantize(const TS* __restrict__ src, const W
   const float inv = inv_unit(m.unit);
   const float maxlvl = (float)max_level(bits);
   // generic items always use the unicast mappings (sub-word stores have no multimem form)
-  DstSet du = ds;
-  du.mc = nullptr;
+  const DST du = unicast_of(ds);
   if (lane_id() == 0) dst_st_v2(du, it.meta_off, __float_as_uint(m.unit), __float_as_uint(m.min));
   for (uint32_t g = lane_id(); g < ng; g += 32) {
     float x[8];
@@ -350,7 +402,12 @@ __device__ __noinline__ void bucket_quantize(const TS* __restrict__ src, const W
     for (int j = 0; j < 8; ++j) u[j] = (j < nv) ? level_magic<true>(x[j], m.min, inv, r[j], maxlvl) : CGX_MAGIC;
     uint32_t lo, hi;
     pack_magic<0>(u, bits, lo, hi);
-    store_word<0>(du, it.pay_off, g, bits, lo, hi);
+    // byte-granular store (a bucket's payload may start at any byte offset)
+    {
+      const uint64_t w = (uint64_t)lo | ((uint64_t)hi << 32);
+      const uint32_t o = it.pay_off + g * (uint32_t)bits;
+      for (int t = 0; t < bits; ++t) dst_st_u8(du, o + t, (uint32_t)(w >> (8 * t)) & 0xFFu);
+    }
     if (self_out != nullptr) {
       float dec[8];
 #pragma unroll
@@ -366,12 +423,12 @@ __device__ __noinline__ void bucket_recv(const SrcSet ss, const WarpItem it, TO*
   const uint32_t n = item_n(it);
   const int bits = item_bits(it);
   const uint32_t ng = div_up(n, 8u);
+  SrcSet s2 = ss;
+  s2.skip = -1;
   for (uint32_t g = lane_id(); g < ng; g += 32) {
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = 0.f;
-    SrcSet s2 = ss;
-    s2.skip = -1;
     bucket_add_sources(s2, it, g, bits, x);  // 0 + d == d exactly
     store8_scalar<TO>(out + g * 8u, (int)min(8u, n - g * 8u), x);
   }
@@ -381,8 +438,8 @@ __device__ __noinline__ void bucket_recv(const SrcSet ss, const WarpItem it, TO*
 // raw (uncompressed) items: n <= 512 elements travelling as T
 // ======================================================================================
 // 8 values -> 8 T on the wire (16 B-aligned records): 2 x 16 B for fp32, 1 x 16 B otherwise
-template <typename T>
-__device__ __forceinline__ void raw_wire_store(const DstSet& ds, uint32_t off, const float (&v)[8]) {
+template <typename T, typename DST>
+__device__ __forceinline__ void raw_wire_store(const DST& ds, uint32_t off, const float (&v)[8]) {
   if (sizeof(T) == 4) {
     dst_st_v4(ds, off, pack16<T>(v));
     dst_st_v4(ds, off + 16u, pack16<T>(v + 4));
@@ -399,27 +456,19 @@ __device__ __forceinline__ void raw_wire_load(const uint8_t* p, float (&v)[8]) {
     unpack16<T>(ld_sys_v4(p), v);
   }
 }
-// what a receiver reads back: the value rounded to T
-template <typename T>
-__device__ __forceinline__ float round_to(float v) {
-  return DT<T>::to_float(DT<T>::from_float(v));
-}
 
-// Full raw item (512 elements). MODE 0: push (phase A / one-shot 1): dst <- T(src * prescale)
-//                               MODE 1: reduce (phase B): own + sum(sources) -> own, dst
-//                               MODE 2: receive: out <- source (ss.n == 1) or sum of all sources
-template <typename T, int MODE>
-__device__ __forceinline__ void raw_full(T* __restrict__ blk, const WarpItem& it, float prescale, const SrcSet& ss,
-                                         const DstSet& ds) {
-  float x[2][8];
-  if (MODE == 2) {
+// Full raw item (512 elements, vector-aligned gradients); x = the item's raw loaded values (MODE 0/1)
+//   MODE 0: push (phase A / one-shot 1): dst <- T(x * prescale)
+//   MODE 1: reduce (phase B): x * prescale + sum(sources) -> own, dst
+//   MODE 2: receive: out <- source (ss.n == 1) or sum of all sources
+// (x may have more than 2 rows -- the prefetch buffer of a 1024 slice -- only rows 0 and 1 are used)
+template <typename T, int MODE, int ROWS, typename DST>
+__device__ __forceinline__ void raw_full_x(float (&x)[ROWS][8], T* __restrict__ blk, const WarpItem& it,
+                                           float prescale, const SrcSet& ss, const DST& ds) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < 2; ++k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[k][j] = 0.f;
-  } else {
-    slice_load<T, 2>(blk, prescale, x);
-  }
+    for (int j = 0; j < 8; ++j) x[k][j] = MODE == 2 ? 0.f : __fmul_rn(x[k][j], prescale);
   if (MODE != 0) {
     for (int q = 0; q < ss.n; ++q) {
       if (q == ss.skip) continue;
@@ -435,9 +484,21 @@ __device__ __forceinline__ void raw_full(T* __restrict__ blk, const WarpItem& it
   }
   if (MODE != 2) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) raw_wire_store<T>(ds, it.meta_off + ((uint32_t)k * 32u + lane_id()) * 8u * sizeof(T), x[k]);
+    for (int k = 0; k < 2; ++k)
+      raw_wire_store<T>(ds, it.meta_off + ((uint32_t)k * 32u + lane_id()) * 8u * (uint32_t)sizeof(T), x[k]);
   }
-  if (MODE != 0) slice_store<T, 2>(blk, x);
+  if (MODE != 0) {
+    T* o = blk + lane_id() * 8u;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) store8_vec<T>(o + k * 256, x[k]);
+  }
+}
+// rows 0..1 of a (possibly larger) register buffer <- the 512 elements of a raw item
+template <typename T, int ROWS>
+__device__ __forceinline__ void raw_load_vec(const T* __restrict__ src, float (&x)[ROWS][8]) {
+  const T* p = src + lane_id() * 8u;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) load8_vec<T>(p + k * 256, x[k]);
 }
 
 // In-switch reduction of a full raw item (NVLS): every rank staged T(src * prescale) at the same
@@ -464,13 +525,13 @@ __device__ __forceinline__ void raw_full_mc_reduce(T* __restrict__ blk, const Wa
   }
 }
 
-// raw tail (< 512 elements) or anything the vector path cannot take: element-wise, cold
-template <typename T>
-__device__ __noinline__ void raw_tail(T* __restrict__ blk, const WarpItem it, float prescale, const SrcSet ss,
-                                      const DstSet ds, int mode) {
+// raw tail (< 512 elements) or a full raw item with unaligned gradients: element-wise, cold.
+// mode as in raw_full_x.
+template <typename T, typename DST>
+__device__ __noinline__ void raw_generic(T* __restrict__ blk, const WarpItem it, float prescale, const SrcSet ss,
+                                         const DST ds, int mode) {
   const uint32_t n = item_n(it);
-  DstSet du = ds;
-  du.mc = nullptr;
+  const DST du = unicast_of(ds);
   for (uint32_t i = lane_id(); i < n; i += 32) {
     float x = mode == 2 ? 0.f : __fmul_rn(DT<T>::to_float(blk[i]), prescale);
     if (mode != 0) {
@@ -490,15 +551,11 @@ __device__ __noinline__ void raw_tail(T* __restrict__ blk, const WarpItem it, fl
     }
     const T t = DT<T>::from_float(x);
     if (mode != 2) {
-      for (int q = 0; q <= du.n; ++q) {
-        // q == n: the optional extra local copy
-        if (q == du.skip || (q == du.n && du.local == nullptr)) continue;
-        T* d = reinterpret_cast<T*>((q == du.n ? du.local : du.bases[q]) + du.off + it.meta_off) + i;
-        if (sizeof(T) == 4)
-          st_u32(d, *reinterpret_cast<const uint32_t*>(&t));
-        else
-          st_u16(d, *reinterpret_cast<const uint16_t*>(&t));
-      }
+      const uint32_t o = it.meta_off + i * (uint32_t)sizeof(T);
+      if (sizeof(T) == 4)
+        dst_st_u32(du, o, *reinterpret_cast<const uint32_t*>(&t));
+      else
+        dst_st_u16(du, o, *reinterpret_cast<const uint16_t*>(&t));
     }
     if (mode != 0) blk[i] = t;
   }

@@ -37,12 +37,17 @@ constexpr uint32_t kMagicBits = 0x4B000000u;  // float bits of 2^23: 2^23 + q ha
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // ---- where packed data goes ------------------------------------------------
-// Destination set of a store: ONE multicast address (NVLS: the switch replicates the write into
-// every rank's copy of the heap), or the same offset in `n` peer-mapped heaps (minus `skip`).
-struct DstSet {
+// ONE destination: a plain (local or peer-mapped) pointer -- SRA phase A, staging, standalone kernels.
+struct OneDst {
+  uint8_t* p;  // base of the destination slot
+};
+// MANY destinations -- SRA phase B, one-shot phase 1: ONE multicast address (NVLS: the switch
+// replicates the write into every rank's copy of the heap), or the same offset in `n`
+// peer-mapped heaps (minus `skip`), plus an optional extra plain copy.
+struct MultiDst {
   uint8_t* const* bases;  // [n] region bases (kernel parameter space)
   uint8_t* mc;            // multicast alias of the region, or nullptr
-  uint32_t off;           // byte offset added to every base (slot of the writer + item offset)
+  uint32_t off;           // byte offset added to every base (slot of the writer)
   int n;
   int skip;               // index not to write (-1: none)
   uint8_t* local;         // additional plain store into this (local) region base, or nullptr
@@ -113,11 +118,30 @@ __device__ __forceinline__ uint4 mc_ld_reduce_v4<__nv_bfloat16>(const void* p) {
   return v;
 }
 
-#define CGX_FOR_DST(ds, q) \
-  for (int q = 0; q < (ds).n; ++q) \
+// (not unrolled: the bases come straight from the constant bank, one LDC per store; unrolling makes
+// ptxas hoist W pointers into registers it does not have)
+#define CGX_FOR_DST(ds, q)                         \
+  _Pragma("unroll 1") for (int q = 0; q < (ds).n; ++q) \
     if (q != (ds).skip)
 
-__device__ __forceinline__ void dst_st_u32(const DstSet& ds, uint32_t off, uint32_t v) {
+__device__ __forceinline__ void dst_st_u8(const OneDst& ds, uint32_t off, uint32_t v) { st_u8(ds.p + off, v); }
+__device__ __forceinline__ void dst_st_u16(const OneDst& ds, uint32_t off, uint32_t v) { st_u16(ds.p + off, v); }
+__device__ __forceinline__ void dst_st_u32(const OneDst& ds, uint32_t off, uint32_t v) { st_u32(ds.p + off, v); }
+__device__ __forceinline__ void dst_st_v2(const OneDst& ds, uint32_t off, uint32_t a, uint32_t b) {
+  st_v2(ds.p + off, a, b);
+}
+__device__ __forceinline__ void dst_st_v4(const OneDst& ds, uint32_t off, const uint4& v) { st_v4(ds.p + off, v); }
+
+// sub-word stores have no multimem form: always through the unicast mappings
+__device__ __forceinline__ void dst_st_u8(const MultiDst& ds, uint32_t off, uint32_t v) {
+  CGX_FOR_DST(ds, q) st_u8(ds.bases[q] + ds.off + off, v);
+  if (ds.local) st_u8(ds.local + ds.off + off, v);
+}
+__device__ __forceinline__ void dst_st_u16(const MultiDst& ds, uint32_t off, uint32_t v) {
+  CGX_FOR_DST(ds, q) st_u16(ds.bases[q] + ds.off + off, v);
+  if (ds.local) st_u16(ds.local + ds.off + off, v);
+}
+__device__ __forceinline__ void dst_st_u32(const MultiDst& ds, uint32_t off, uint32_t v) {
   if (ds.mc) {
     mc_st_u32(ds.mc + ds.off + off, v);
   } else {
@@ -125,7 +149,7 @@ __device__ __forceinline__ void dst_st_u32(const DstSet& ds, uint32_t off, uint3
   }
   if (ds.local) st_u32(ds.local + ds.off + off, v);
 }
-__device__ __forceinline__ void dst_st_v2(const DstSet& ds, uint32_t off, uint32_t a, uint32_t b) {
+__device__ __forceinline__ void dst_st_v2(const MultiDst& ds, uint32_t off, uint32_t a, uint32_t b) {
   if (ds.mc) {
     mc_st_v2(ds.mc + ds.off + off, a, b);
   } else {
@@ -133,7 +157,7 @@ __device__ __forceinline__ void dst_st_v2(const DstSet& ds, uint32_t off, uint32
   }
   if (ds.local) st_v2(ds.local + ds.off + off, a, b);
 }
-__device__ __forceinline__ void dst_st_v4(const DstSet& ds, uint32_t off, const uint4& v) {
+__device__ __forceinline__ void dst_st_v4(const MultiDst& ds, uint32_t off, const uint4& v) {
   if (ds.mc) {
     mc_st_v4(ds.mc + ds.off + off, v);
   } else {
@@ -141,6 +165,14 @@ __device__ __forceinline__ void dst_st_v4(const DstSet& ds, uint32_t off, const 
   }
   if (ds.local) st_v4(ds.local + ds.off + off, v);
 }
+// the same destinations, unicast only (generic paths whose stores have no multimem form)
+__device__ __forceinline__ OneDst unicast_of(const OneDst& ds) { return ds; }
+__device__ __forceinline__ MultiDst unicast_of(const MultiDst& ds) {
+  MultiDst d = ds;
+  d.mc = nullptr;
+  return d;
+}
+
 // ---- 8 elements <-> registers ---------------------------------------------------
 // vector access needs (address % 32 == 0) for fp32 (256-bit LDG/STG) and % 16 for 16-bit types
 template <typename T>
@@ -255,29 +287,30 @@ __device__ __forceinline__ float level_magic(float x, float mn, float inv, float
   return __fadd_rz(t, CGX_MAGIC);
 }
 
-// Horner packing of 8 magic floats; the 0x4B000000 of every term adds up to a constant
+// Packing of 8 magic floats into a word: shift-adds in a depth-3 tree (7 IMADs, no masking);
+// the 0x4B000000 of every term adds up to a constant that is subtracted once.
 template <int KB>
 __device__ __forceinline__ void pack_magic(const float (&u)[8], int bits, uint32_t& lo, uint32_t& hi) {
   if constexpr (KB >= 1 && KB <= 4) {
-    uint32_t w = __float_as_uint(u[7]);
+    uint32_t a[4];
 #pragma unroll
-    for (int j = 6; j >= 0; --j) w = (w << KB) + __float_as_uint(u[j]);
-    // the eight 0x4B000000 terms add up to a constant for KB == 4 (sum_j 0x4B000000 << 4j mod 2^32);
-    // for narrower words they never reach the low 8*KB bits
+    for (int j = 0; j < 4; ++j) a[j] = (__float_as_uint(u[2 * j + 1]) << KB) + __float_as_uint(u[2 * j]);
+    const uint32_t b0 = (a[1] << (2 * KB)) + a[0], b1 = (a[3] << (2 * KB)) + a[2];
+    const uint32_t w = (b1 << (4 * KB)) + b0;
+    // sum_j (0x4B000000 << 4j) mod 2^32 for KB == 4; for narrower words the magic bits never reach
+    // the low 8*KB bits
     if constexpr (KB == 4)
       lo = w - 0xFB000000u;
     else
       lo = w & ((1u << (8 * KB)) - 1u);
     hi = 0;
   } else if constexpr (KB == 8) {
-    uint32_t a = __float_as_uint(u[3]), b = __float_as_uint(u[7]);
-#pragma unroll
-    for (int j = 2; j >= 0; --j) {
-      a = (a << 8) + __float_as_uint(u[j]);
-      b = (b << 8) + __float_as_uint(u[4 + j]);
-    }
-    lo = a - kMagicBits;
-    hi = b - kMagicBits;
+    const uint32_t a0 = (__float_as_uint(u[1]) << 8) + __float_as_uint(u[0]);
+    const uint32_t a1 = (__float_as_uint(u[3]) << 8) + __float_as_uint(u[2]);
+    const uint32_t a2 = (__float_as_uint(u[5]) << 8) + __float_as_uint(u[4]);
+    const uint32_t a3 = (__float_as_uint(u[7]) << 8) + __float_as_uint(u[6]);
+    lo = ((a1 << 16) + a0) - kMagicBits;
+    hi = ((a3 << 16) + a2) - kMagicBits;
   } else {
     uint64_t w = 0;
 #pragma unroll
@@ -318,13 +351,13 @@ __device__ __forceinline__ void unpack_magic(uint32_t lo, uint32_t hi, int bits,
 template <int KB>
 __device__ __forceinline__ void load_word(const uint8_t* pay, uint32_t g, int bits, uint32_t& lo, uint32_t& hi) {
   hi = 0;
-  if (KB == 8) {
+  if constexpr (KB == 8) {
     const uint2 v = ld_sys_v2(pay + (size_t)g * 8u);
     lo = v.x;
     hi = v.y;
-  } else if (KB == 4) {
+  } else if constexpr (KB == 4) {
     lo = ld_sys_u32(pay + (size_t)g * 4u);
-  } else if (KB == 2) {
+  } else if constexpr (KB == 2) {
     lo = ld_sys_u16(pay + (size_t)g * 2u);
   } else {
     const uint8_t* p = pay + (size_t)g * bits;
@@ -335,34 +368,34 @@ __device__ __forceinline__ void load_word(const uint8_t* pay, uint32_t g, int bi
   }
 }
 
-// store the packed word of group g (byte offset `pay_off` of the payload start inside the set)
-template <int KB>
-__device__ __forceinline__ void store_word(const DstSet& ds, uint32_t pay_off, uint32_t g, int bits, uint32_t lo,
+// store the packed word of group g (byte offset `pay_off` of the payload start inside the slot)
+template <int KB, typename DST>
+__device__ __forceinline__ void store_word(const DST& ds, uint32_t pay_off, uint32_t g, int bits, uint32_t lo,
                                            uint32_t hi) {
-  if (KB == 8) {
+  if constexpr (KB == 8) {
     dst_st_v2(ds, pay_off + g * 8u, lo, hi);
-  } else if (KB == 4) {
+  } else if constexpr (KB == 4) {
     dst_st_u32(ds, pay_off + g * 4u, lo);
-  } else if (KB == 2) {
+  } else if constexpr (KB == 2) {
     // two neighbouring groups -> one 32-bit store by the even lane (multimem has no 16-bit form)
     const uint32_t nb = __shfl_down_sync(kAll, lo, 1);
     if ((lane_id() & 1u) == 0) dst_st_u32(ds, pay_off + g * 2u, lo | (nb << 16));
   } else {
-    // other widths: byte stores through the unicast mappings (no multimem form; the host never
-    // hands out a multicast alias for plans with such widths)
+    // other widths: byte stores through the unicast mappings (the host never hands out a
+    // multicast alias for plans with such widths)
     const uint64_t w = (uint64_t)lo | ((uint64_t)hi << 32);
-    const uint32_t o = ds.off + pay_off + g * (uint32_t)bits;
-    for (int t = 0; t < bits; ++t) {
-      const uint32_t byte = (uint32_t)(w >> (8 * t)) & 0xFFu;
-      CGX_FOR_DST(ds, q) st_u8(ds.bases[q] + o + t, byte);
-      if (ds.local) st_u8(ds.local + o + t, byte);
-    }
+    const uint32_t o = pay_off + g * (uint32_t)bits;
+    for (int t = 0; t < bits; ++t) dst_st_u8(ds, o + t, (uint32_t)(w >> (8 * t)) & 0xFFu);
   }
 }
 
-// stochastic rounding offsets of one group from its Philox word (host twin: rounding_from_bits)
+// stochastic rounding offsets of one group from its Philox word (host twin: rounding_from_bits).
+// The keys are made opaque per call: otherwise the ten round keys become loop invariants that the
+// compiler hoists out of the item loops -- 18 registers the deterministic path needs.
 __device__ __forceinline__ void rounding8(const RngKey& rng, uint32_t first_elem, float (&r)[8]) {
-  const Philox4 a = rounding_bits(rng, first_elem);
+  uint32_t k0 = rng.seed_lo ^ (rng.stream * 0x9E3779B9u), k1 = rng.seed_hi;
+  asm volatile("" : "+r"(k0), "+r"(k1));
+  const Philox4 a = philox4x32_10(first_elem, 0u, 0u, rng.seq, k0, k1);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint32_t h = (a.v[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;

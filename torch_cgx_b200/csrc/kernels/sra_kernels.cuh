@@ -78,8 +78,79 @@ __device__ __forceinline__ bool wait_peers(const uint32_t* my_flags, int W, int 
   return __all_sync(kAll, ok);
 }
 
+// ---- per-lane item cache ----------------------------------------------------------------
+// The items of ALL chunks of this lane are copied to shared memory once, in the order
+// s = 0 (my own chunk), 1, .., W-1 (chunk (rank + s) % W): an item descriptor then costs one
+// LDS instead of a dependent global load in front of every data load. Lists longer than the
+// cache (huge messages on few lanes) read the remainder from global memory.
+constexpr uint32_t kSmemItems = 1024;
+
+struct LaneItems {
+  WarpItem items[kSmemItems];
+  uint32_t pre[kMaxPeers + 1];   // pre[s]: flat index of the first item of chunk (rank + s) % W
+  uint32_t gfirst[kMaxPeers];    // its index in the global item table
+};
+
+__device__ __forceinline__ void lane_items_load(LaneItems& li, const SraParams& p, int nchunks) {
+  const int lane = blockIdx.x, G = p.lanes;
+  if (threadIdx.x < (uint32_t)nchunks) {
+    const int q = nchunks == 1 ? 0 : (p.rank + (int)threadIdx.x) % p.world;
+    const uint32_t a = p.item_first[q * G + lane];
+    li.gfirst[threadIdx.x] = a;
+    li.pre[threadIdx.x + 1] = p.item_first[q * G + lane + 1] - a;  // count, turned into a prefix below
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    li.pre[0] = 0;
+    for (int s = 0; s < nchunks; ++s) li.pre[s + 1] += li.pre[s];
+  }
+  __syncthreads();
+  const uint32_t total = min(li.pre[nchunks], kSmemItems);
+  for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+    int s = 0;
+    while (i >= li.pre[s + 1]) ++s;
+    li.items[i] = p.items[li.gfirst[s] + (i - li.pre[s])];
+  }
+  __syncthreads();
+}
+// item with flat index i, known to belong to chunk slot s
+__device__ __forceinline__ WarpItem lane_item(const LaneItems& li, const SraParams& p, uint32_t i, int s) {
+  if (i < kSmemItems) return li.items[i];
+  return p.items[li.gfirst[s] + (i - li.pre[s])];
+}
+
+// Fetch item `i` of a flat range and, if it is a hot kind with vector-aligned gradients, issue
+// the loads of its values (they are consumed one loop iteration later: the data of the NEXT item
+// is in flight while the current one is processed). hot: 0 cold item (loads its own data),
+// 1 full slice, 2 full raw item. Plain scalars/arrays on purpose: a struct here ends up in
+// local memory.
+template <typename T, int GPL>
+__device__ __forceinline__ void prefetch_values(const LaneItems& li, const SraParams& p, uint32_t i, uint32_t end,
+                                                bool want_raw, WarpItem& it, int& s, int& hot,
+                                                float (&x)[GPL][8]) {
+  hot = 0;
+  if (i >= end) return;
+  while (i >= li.pre[s + 1]) ++s;
+  it = lane_item(li, p, i, s);
+  const T* src = reinterpret_cast<const T*>(p.data) + it.elem_off;
+  const uint32_t kind = item_kind(it);
+  if (!group_aligned<T>(src)) return;
+  if (kind == kItemFull) {
+    hot = 1;
+    slice_load_vec<T, GPL>(src, x);
+  } else if (kind == kItemRaw && want_raw) {
+    hot = 2;
+    raw_load_vec<T, GPL>(src, x);
+  }
+}
+
+#define CGX_COPY_SLICE(dst, src)                 \
+  _Pragma("unroll") for (int k_ = 0; k_ < GPL; ++k_) \
+      _Pragma("unroll") for (int j_ = 0; j_ < 8; ++j_)(dst)[k_][j_] = (src)[k_][j_]
+
 template <typename T, int KB, int GPL>
 __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const __grid_constant__ SraParams p) {
+  __shared__ LaneItems li;
   __shared__ int s_abort;
   const int lane = blockIdx.x;
   const int r = p.rank, W = p.world, G = p.lanes;
@@ -89,43 +160,60 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
   RngKey rng = p.rng;
   rng.seq += epoch - p.epoch_hint;  // graph replays advance the random stream
   if (threadIdx.x == 0) s_abort = 0;
-  __syncthreads();
+  lane_items_load(li, p, W);
   trace_mark(p.trace, lane, 0, true);
 
   const SrcSet no_src{nullptr, 0u, 0, -1};
+  const uint32_t own_end = li.pre[1], total = li.pre[W];
 
   // ------------------------------------------------------------------ phase A
+  // my copy of every other chunk -> its owner (items of all destinations dealt round-robin to
+  // the warps); with the in-switch reduction the full raw items of ALL chunks are staged locally
   {
     rng.stream = (uint32_t)r * 2u;
-    uint32_t base = 0;  // items dealt so far: item i of the phase goes to warp (i % kSraWarps)
-    // with the in-switch reduction my own chunk's full raw items are staged too
-    for (int s = p.mc_reduce ? 0 : 1; s < W; ++s) {
-      const int dstp = (r + s) % W;
-      const uint32_t i0 = p.item_first[dstp * G + lane];
-      const uint32_t cnt = p.item_first[dstp * G + lane + 1] - i0;
-      const DstSet push{&p.recv1[dstp], nullptr, (uint32_t)r * p.slot_bytes, 1, -1, nullptr};
-      const DstSet stage{&p.recv2[r], nullptr, (uint32_t)dstp * p.slot_bytes, 1, -1, nullptr};
-      for (uint32_t i = (warp - base) & (kSraWarps - 1); i < cnt; i += kSraWarps) {
-        const WarpItem it = p.items[i0 + i];
-        const uint32_t kind = item_kind(it);
-        T* blk = data + it.elem_off;
-        if (p.mc_reduce) {
-          if (kind == kItemRaw) {
-            raw_full<T, 0>(blk, it, p.prescale, no_src, stage);
-            continue;
-          }
-          if (s == 0) continue;
+    const uint32_t begin = p.mc_reduce ? 0u : own_end;
+    WarpItem it, itn;
+    int cs = p.mc_reduce ? 0 : 1, hot, hotn;
+    float x[GPL][8], xn[GPL][8];
+    uint32_t i = begin + warp;
+    prefetch_values<T, GPL>(li, p, i, total, true, it, cs, hot, x);
+    while (i < total) {
+      int csn = cs;
+      prefetch_values<T, GPL>(li, p, i + kSraWarps, total, true, itn, csn, hotn, xn);
+      const uint32_t kind = item_kind(it);
+      const int dstp = (r + cs) % W;
+      T* blk = data + it.elem_off;
+      const OneDst push{p.recv1[dstp] + (size_t)r * p.slot_bytes};
+      bool done = false;
+      if (p.mc_reduce) {
+        if (kind == kItemRaw) {
+          const OneDst stage{p.recv2[r] + (size_t)dstp * p.slot_bytes};
+          if (hot == 2)
+            raw_full_x<T, 0, GPL>(x, blk, it, p.prescale, no_src, stage);
+          else
+            raw_generic<T>(blk, it, p.prescale, no_src, stage, 0);
+          done = true;
+        } else if (cs == 0) {
+          done = true;  // my own chunk: nothing else to send
         }
-        if (kind == kItemFull)
-          full_send<T, T, KB, GPL, false>(blk, it, p.prescale, rng, push, nullptr);
-        else if (kind == kItemRaw)
-          raw_full<T, 0>(blk, it, p.prescale, no_src, push);
-        else if (kind == kItemBucket)
-          bucket_quantize<T, T>(blk, it, p.prescale, rng, no_src, push, nullptr);
-        else
-          raw_tail<T>(blk, it, p.prescale, no_src, push, 0);
       }
-      base += cnt;
+      if (!done) {
+        if (hot == 1)
+          full_send_x<T, KB, GPL, false, true>(x, it, p.prescale, rng, push, (T*)nullptr);
+        else if (hot == 2)
+          raw_full_x<T, 0, GPL>(x, blk, it, p.prescale, no_src, push);
+        else if (kind == kItemFull)
+          full_send_unaligned<T, T, KB, GPL, false>(blk, it, p.prescale, rng, push, (T*)nullptr);
+        else if (kind == kItemBucket)
+          bucket_quantize<T, T>(blk, it, p.prescale, rng, no_src, push, (T*)nullptr);
+        else
+          raw_generic<T>(blk, it, p.prescale, no_src, push, 0);
+      }
+      it = itn;
+      cs = csn;
+      hot = hotn;
+      CGX_COPY_SLICE(x, xn);
+      i += kSraWarps;
     }
     __syncthreads();
     if (warp == 0) signal_peers(p.flags1, W, r, p.flag_stride, lane, epoch);
@@ -134,9 +222,7 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
 
   // ------------------------------------------------------------------ phase B
   {
-    const uint32_t i0 = p.item_first[r * G + lane];
-    const uint32_t cnt = p.item_first[r * G + lane + 1] - i0;
-    if (warp == 0 && cnt > 0) {
+    if (warp == 0 && own_end > 0) {
       if (!wait_peers(p.flags1[r], W, r, p.flag_stride, lane, epoch, p.timeout_ns, p.status, kSraTimeoutPhase1))
         s_abort = 1;
     }
@@ -145,22 +231,35 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
     if (!s_abort) {
       rng.stream = (uint32_t)r * 2u + 1u;
       const SrcSet ss{p.recv1[r], p.slot_bytes, W, r};
-      const DstSet ds{p.recv2, p.mc_recv2, (uint32_t)r * p.slot_bytes, W, r, nullptr};
-      for (uint32_t i = warp; i < cnt; i += kSraWarps) {
-        const WarpItem it = p.items[i0 + i];
+      const MultiDst ds{p.recv2, p.mc_recv2, (uint32_t)r * p.slot_bytes, W, r, nullptr};
+      // the registers of this phase belong to the peers' words: the NEXT item's own values are only
+      // pulled towards L2 (prefetch.global.L2), the current item's are loaded at the top
+      for (uint32_t i = warp; i < own_end; i += kSraWarps) {
+        const WarpItem it = lane_item(li, p, i, 0);
         const uint32_t kind = item_kind(it);
         T* blk = data + it.elem_off;
-        if (kind == kItemFull)
-          full_reduce<T, KB, GPL>(blk, it, p.prescale, rng, ss, ds);
-        else if (kind == kItemRaw) {
-          if (p.mc_reduce)
-            raw_full_mc_reduce<T>(blk, it, p.mc_recv2 + (size_t)r * p.slot_bytes);
+        const bool al = group_aligned<T>(blk);
+        float x[GPL][8];
+        if (al && kind == kItemFull) slice_load_vec<T, GPL>(blk, x);
+        if (al && kind == kItemRaw && !p.mc_reduce) raw_load_vec<T, GPL>(blk, x);
+        if (i + kSraWarps < own_end) {
+          const WarpItem itn = lane_item(li, p, i + kSraWarps, 0);
+          if (!(p.mc_reduce && item_kind(itn) == kItemRaw)) slice_prefetch_l2<T, GPL>(data + itn.elem_off);
+        }
+        if (kind == kItemFull) {
+          if (al)
+            full_reduce_x<T, KB, GPL, true>(x, blk, it, p.prescale, rng, ss, ds);
           else
-            raw_full<T, 1>(blk, it, p.prescale, ss, ds);
-        } else if (kind == kItemBucket)
+            full_reduce_unaligned<T, KB, GPL>(blk, it, p.prescale, rng, ss, ds);
+        } else if (kind == kItemBucket) {
           bucket_quantize<T, T>(blk, it, p.prescale, rng, ss, ds, blk);
-        else
-          raw_tail<T>(blk, it, p.prescale, ss, ds, 1);
+        } else if (kind == kItemRaw && p.mc_reduce) {
+          raw_full_mc_reduce<T>(blk, it, p.mc_recv2 + (size_t)r * p.slot_bytes);
+        } else if (kind == kItemRaw && al) {
+          raw_full_x<T, 1, GPL>(x, blk, it, p.prescale, ss, ds);
+        } else {
+          raw_generic<T>(blk, it, p.prescale, ss, ds, 1);
+        }
       }
     }
     __syncthreads();
@@ -170,22 +269,16 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
 
   // ------------------------------------------------------------------ phase C
   if (!s_abort) {
-    // lane s of every warp looks after chunk (r + s) % W: its item range and rotation
-    const int myq = (r + (int)wl) % W;
+    // lane s of every warp looks after chunk slot s: polls its flag; chunks are decoded in
+    // order of arrival. rot keeps the round-robin over warps continuous across chunks.
     const bool mine = wl >= 1 && wl < (uint32_t)W;
-    const uint32_t my_i0 = mine ? p.item_first[myq * G + lane] : 0u;
-    const uint32_t my_cnt = mine ? p.item_first[myq * G + lane + 1] - my_i0 : 0u;
-    uint32_t pre = my_cnt;  // inclusive prefix sum over lanes -> rotation keeps the warps balanced
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(kAll, pre, o);
-      if ((int)wl >= o) pre += v;
-    }
-    const uint32_t my_rot = pre - my_cnt;
-    const uint32_t* my_flag = p.flags2[r] + (size_t)myq * p.flag_stride + lane;
+    const uint32_t my_cnt = mine ? li.pre[wl + 1] - li.pre[wl] : 0u;
+    const uint32_t my_rot = mine ? li.pre[wl] - own_end : 0u;
+    const uint32_t* my_flag = p.flags2[r] + (size_t)((r + (int)wl) % W) * p.flag_stride + lane;
     uint32_t pending = __ballot_sync(kAll, my_cnt > 0);
     uint32_t spins = 0;
     uint64_t t0 = 0;
+    const OneDst none{nullptr};
     while (pending) {
       const bool rdy = ((pending >> wl) & 1u) && (int32_t)(ld_acquire_sys(my_flag) - epoch) >= 0;
       uint32_t ready = __ballot_sync(kAll, rdy);
@@ -193,10 +286,9 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
         if ((++spins & 0x3FFu) == 0) {
           const uint64_t now = globaltimer_ns();
           if (t0 == 0) t0 = now;
-          const bool expired = now - t0 > p.timeout_ns;
-          if (__any_sync(kAll, expired)) {
+          if (__any_sync(kAll, now - t0 > p.timeout_ns)) {
             if (wl == (uint32_t)__ffs(pending) - 1u)
-              *p.status = kSraTimeoutPhase2 | ((uint32_t)myq << 8) | ((uint32_t)lane << 16);
+              *p.status = kSraTimeoutPhase2 | ((uint32_t)((r + (int)wl) % W) << 8) | ((uint32_t)lane << 16);
             break;
           }
         }
@@ -208,22 +300,52 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
         const int s = __ffs(ready) - 1;
         ready &= ready - 1;
         const int q = (r + s) % W;
-        const uint32_t i0 = __shfl_sync(kAll, my_i0, s);
-        const uint32_t cnt = __shfl_sync(kAll, my_cnt, s);
         const uint32_t rot = __shfl_sync(kAll, my_rot, s);
-        const SrcSet ss{p.recv2[r] + (size_t)q * p.slot_bytes, 0u, 1, -1};
-        for (uint32_t i = (warp - rot) & (kSraWarps - 1); i < cnt; i += kSraWarps) {
-          const WarpItem it = p.items[i0 + i];
+        const uint32_t end = li.pre[s + 1];
+        const uint8_t* slot = p.recv2[r] + (size_t)q * p.slot_bytes;
+        const SrcSet ss{slot, 0u, 1, -1};
+        // software pipeline: the packed words of the next item are in flight while this one decodes
+        uint32_t i = li.pre[s] + ((warp - rot) & (kSraWarps - 1));
+        WarpItem it, itn;
+        SliceWords<GPL> w, wn;
+        bool hot = false, hotn = false;
+        if (i < end) {
+          it = lane_item(li, p, i, s);
+          hot = item_kind(it) == kItemFull && group_aligned<T>(data + it.elem_off);
+          if (hot) slice_fetch<KB, GPL>(slot, it.meta_off, it.pay_off, item_lpb_log2(it), KB ? KB : item_bits(it), w);
+        }
+        while (i < end) {
+          const uint32_t in = i + kSraWarps;
+          hotn = false;
+          if (in < end) {
+            itn = lane_item(li, p, in, s);
+            hotn = item_kind(itn) == kItemFull && group_aligned<T>(data + itn.elem_off);
+            if (hotn)
+              slice_fetch<KB, GPL>(slot, itn.meta_off, itn.pay_off, item_lpb_log2(itn), KB ? KB : item_bits(itn), wn);
+          }
           const uint32_t kind = item_kind(it);
           T* blk = data + it.elem_off;
-          if (kind == kItemFull)
-            full_recv<T, KB, GPL>(ss, it, blk);
-          else if (kind == kItemRaw)
-            raw_full<T, 2>(blk, it, 1.0f, ss, DstSet{nullptr, nullptr, 0u, 0, -1, nullptr});
-          else if (kind == kItemBucket)
+          if (hot) {
+            full_recv_w<T, KB, GPL, true>(w, it, blk);
+          } else if (kind == kItemFull) {
+            full_recv_unaligned<T, KB, GPL>(ss, it, blk);
+          } else if (kind == kItemRaw && group_aligned<T>(blk)) {
+            float x[2][8];
+            raw_full_x<T, 2, 2>(x, blk, it, 1.0f, ss, none);
+          } else if (kind == kItemBucket) {
             bucket_recv<T>(ss, it, blk);
-          else
-            raw_tail<T>(blk, it, 1.0f, ss, DstSet{nullptr, nullptr, 0u, 0, -1, nullptr}, 2);
+          } else {
+            raw_generic<T>(blk, it, 1.0f, ss, none, 2);
+          }
+          it = itn;
+#pragma unroll
+          for (int k = 0; k < GPL; ++k) {
+            w.lo[k] = wn.lo[k];
+            w.hi[k] = wn.hi[k];
+            w.pm[k] = wn.pm[k];
+          }
+          hot = hotn;
+          i = in;
         }
       }
     }
@@ -244,6 +366,7 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
 // ===========================================================================
 template <typename T, int KB, int GPL>
 __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(const __grid_constant__ SraParams p) {
+  __shared__ LaneItems li;
   __shared__ int s_abort;
   const int lane = blockIdx.x;
   const int r = p.rank, W = p.world;
@@ -254,31 +377,41 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
   rng.seq += epoch - p.epoch_hint;
   rng.stream = (uint32_t)r * 2u;
   if (threadIdx.x == 0) s_abort = 0;
-  __syncthreads();
+  lane_items_load(li, p, 1);
   trace_mark(p.trace, lane, 0, true);
   const uint32_t region = (epoch & 1u) * p.os_parity_stride;
-  const uint32_t i0 = p.item_first[lane];
-  const uint32_t cnt = p.item_first[lane + 1] - i0;
+  const uint32_t total = li.pre[1];
   const SrcSet no_src{nullptr, 0u, 0, -1};
 
   // ---- phase 1: my image -> slot r of every rank (mine included)
   {
     // with NVLS the switch also delivers my own replica, but asynchronously: my slot is
     // additionally written with a plain local store so that phase 2 never depends on the loopback
-    const DstSet ds{p.recv1, p.mc_recv1, region + (uint32_t)r * p.slot_bytes, W, p.mc_recv1 ? r : -1,
-                    p.mc_recv1 ? p.recv1[r] : nullptr};
-    for (uint32_t i = warp; i < cnt; i += kSraWarps) {
-      const WarpItem it = p.items[i0 + i];
+    const MultiDst ds{p.recv1, p.mc_recv1, region + (uint32_t)r * p.slot_bytes, W, p.mc_recv1 ? r : -1,
+                      p.mc_recv1 ? p.recv1[r] : nullptr};
+    WarpItem it, itn;
+    int cs = 0, csn = 0, hot, hotn;
+    float x[GPL][8], xn[GPL][8];
+    uint32_t i = warp;
+    prefetch_values<T, GPL>(li, p, i, total, true, it, cs, hot, x);
+    while (i < total) {
+      prefetch_values<T, GPL>(li, p, i + kSraWarps, total, true, itn, csn, hotn, xn);
       const uint32_t kind = item_kind(it);
       T* blk = data + it.elem_off;
-      if (kind == kItemFull)
-        full_send<T, T, KB, GPL, false>(blk, it, p.prescale, rng, ds, nullptr);
-      else if (kind == kItemRaw)
-        raw_full<T, 0>(blk, it, p.prescale, no_src, ds);
+      if (hot == 1)
+        full_send_x<T, KB, GPL, false, true>(x, it, p.prescale, rng, ds, (T*)nullptr);
+      else if (hot == 2)
+        raw_full_x<T, 0, GPL>(x, blk, it, p.prescale, no_src, ds);
+      else if (kind == kItemFull)
+        full_send_unaligned<T, T, KB, GPL, false>(blk, it, p.prescale, rng, ds, (T*)nullptr);
       else if (kind == kItemBucket)
-        bucket_quantize<T, T>(blk, it, p.prescale, rng, no_src, ds, nullptr);
+        bucket_quantize<T, T>(blk, it, p.prescale, rng, no_src, ds, (T*)nullptr);
       else
-        raw_tail<T>(blk, it, p.prescale, no_src, ds, 0);
+        raw_generic<T>(blk, it, p.prescale, no_src, ds, 0);
+      it = itn;
+      hot = hotn;
+      CGX_COPY_SLICE(x, xn);
+      i += kSraWarps;
     }
     __syncthreads();
     if (warp == 0) signal_peers(p.flags1, W, r, p.flag_stride, lane, epoch);
@@ -287,7 +420,7 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
 
   // ---- phase 2: all W images (mine was written by this CTA, ordered by the bar.sync above)
   {
-    if (warp == 0 && cnt > 0) {
+    if (warp == 0 && total > 0) {
       if (!wait_peers(p.flags1[r], W, r, p.flag_stride, lane, epoch, p.timeout_ns, p.status, kSraTimeoutPhase1))
         s_abort = 1;
     }
@@ -295,19 +428,24 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
     trace_mark(p.trace, lane, 2);
     if (!s_abort) {
       const SrcSet ss{p.recv1[r] + region, p.slot_bytes, W, -1};
-      const DstSet none{nullptr, nullptr, 0u, 0, -1, nullptr};
-      for (uint32_t i = warp; i < cnt; i += kSraWarps) {
-        const WarpItem it = p.items[i0 + i];
+      const OneDst none{nullptr};
+      for (uint32_t i = warp; i < total; i += kSraWarps) {
+        const WarpItem it = lane_item(li, p, i, 0);
         const uint32_t kind = item_kind(it);
         T* blk = data + it.elem_off;
-        if (kind == kItemFull)
-          full_recv<T, KB, GPL>(ss, it, blk);
-        else if (kind == kItemRaw)
-          raw_full<T, 2>(blk, it, 1.0f, ss, none);
-        else if (kind == kItemBucket)
+        const bool al = group_aligned<T>(blk);
+        if (kind == kItemFull && al) {
+          full_recv_sum<T, KB, GPL, true>(ss, it, blk);
+        } else if (kind == kItemFull) {
+          full_recv_unaligned<T, KB, GPL>(ss, it, blk);
+        } else if (kind == kItemRaw && al) {
+          float x[2][8];
+          raw_full_x<T, 2, 2>(x, blk, it, 1.0f, ss, none);
+        } else if (kind == kItemBucket) {
           bucket_recv<T>(ss, it, blk);
-        else
-          raw_tail<T>(blk, it, 1.0f, ss, none, 2);
+        } else {
+          raw_generic<T>(blk, it, 1.0f, ss, none, 2);
+        }
       }
     }
   }

@@ -68,6 +68,7 @@ class FusedSra {
   // bumped whenever cached DevicePlan pointers become invalid (cache trimmed)
   uint64_t generation() const { return generation_; }
   uint32_t epoch() const { return epoch_; }
+  size_t num_plans() const { return cache_.size(); }
 
  private:
   SymmetricHeap* heap_;
