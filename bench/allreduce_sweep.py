@@ -29,6 +29,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import torch_cgx_b200 as cgx  # noqa: E402
+from torch_cgx_b200.utils.clocks import ClockSampler  # noqa: E402
 
 
 def median(xs):
@@ -70,6 +71,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--bucket-size", type=int, default=512)
+    ap.add_argument("--sizes", default="", help="explicit comma-separated sizes in KB (overrides min/max)")
     ap.add_argument("--with-nccl-sra", action="store_true",
                     help="also time the reference-structure path: SRA over NCCL send/recv + separate kernels")
     args = ap.parse_args()
@@ -92,11 +94,16 @@ def main():
         nccl_sra = dist.new_group(backend="cgx")
         os.environ.pop("CGX_INNER_COMMUNICATOR_TYPE")
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     sizes = []
     s = args.min_kb << 10
     while s <= (args.max_mb << 20):
         sizes.append(s)
         s *= 4
+    if args.sizes:
+        sizes = [int(x) << 10 for x in args.sizes.split(",")]
     rows = []
     for nbytes in sizes:
         n = nbytes // es
@@ -138,8 +145,10 @@ def main():
                     print(json.dumps(r), flush=True)
         del bufs
     if rank == 0:
+        clocks = sampler.stop()
         Path(args.out).parent.mkdir(parents=True, exist_ok=True)
-        Path(args.out).write_text(json.dumps({"world": world, "lanes": be.lanes(), "rows": rows,
+        Path(args.out).write_text(json.dumps({"world": world, "lanes": be.lanes(), "heap": be.heap_kind(),
+                                              "nvls_multicast": be.uses_multicast(), "clocks": clocks, "rows": rows,
                                               "timing": "CUDA events around `iters` back-to-back calls on rotating buffers (> 2x L2 in total), max over ranks, median of 3 repetitions"}, indent=1))
     dist.barrier()
     dist.destroy_process_group()

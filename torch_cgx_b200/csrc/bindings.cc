@@ -16,6 +16,7 @@
 #include <tuple>
 #include <vector>
 
+#include "comm/fd_channel.h"
 #include "common/block_ops.h"
 #include "common/config.h"
 #include "common/layers.h"
@@ -306,8 +307,20 @@ class LocalSraGroup {
                  bool skip_incomplete, bool stochastic, uint64_t seed, uint32_t seq) {
     run(std::move(tensors), layers, average, skip_incomplete, stochastic, seed, seq, false);
   }
+  // fault injection: virtual rank `absent` never launches its kernel (a dead / stuck peer)
+  void allreduce_with_absent_rank(std::vector<at::Tensor> tensors, const std::vector<LayerTuple>& layers,
+                                  int absent) {
+    run(std::move(tensors), layers, false, false, false, 0, 1, false, absent);
+  }
+  void abort_all() {
+    for (auto& h : heaps_) h->request_abort(true);
+  }
+  std::string status(int r) { return fused_[r]->status_message(); }
+  void clear() {
+    for (auto& f : fused_) f->clear_status();
+  }
   void run(std::vector<at::Tensor> tensors, const std::vector<LayerTuple>& layers, bool average,
-           bool skip_incomplete, bool stochastic, uint64_t seed, uint32_t seq, bool oneshot) {
+           bool skip_incomplete, bool stochastic, uint64_t seed, uint32_t seq, bool oneshot, int absent = -1) {
     TORCH_CHECK((int)tensors.size() == world_, "need one tensor per virtual rank");
     const int dt = cgx_dtype(tensors[0]);
     auto specs = to_layers(layers);
@@ -330,6 +343,7 @@ class LocalSraGroup {
     if (fresh_plan)
       for (int r = 0; r < world_; ++r) streams_[r].synchronize();
     for (int r = 0; r < world_; ++r) {
+      if (r == absent) continue;
       const float ps = average ? 1.0f / (float)world_ : 1.0f;
       if (oneshot)
         fused_[r]->run_oneshot(*plans[r], tensors[r].data_ptr(), ps, rng, streams_[r].stream());
@@ -393,6 +407,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("stats", &ProcessGroupCGX::stats)
       .def("reset_stats", &ProcessGroupCGX::reset_stats)
       .def("check_health", &ProcessGroupCGX::check_health)
+      .def("failure", &ProcessGroupCGX::failure)
+      .def("last_lanes", &ProcessGroupCGX::last_lanes)
+      .def("abort", &ProcessGroupCGX::abort, py::call_guard<py::gil_scoped_release>())
+      .def("uses_multicast", [](ProcessGroupCGX& pg) { return pg.uses_multicast(); })
+      .def("heap_kind", [](ProcessGroupCGX& pg) { return pg.heap_kind(); })
       .def("enable_trace", &ProcessGroupCGX::enable_trace)
       .def("read_trace", &ProcessGroupCGX::read_trace);
 
@@ -531,6 +550,20 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("max_resident_ctas", [](int dtype) { return sra_max_resident_ctas(dtype); }, py::arg("dtype") = 0);
 
+  py::class_<FdChannel>(m, "FdChannel")
+      .def(py::init<const std::string&>(), py::arg("hint"))
+      .def("name", &FdChannel::name)
+      .def("send", &FdChannel::try_send, py::arg("peer_name"), py::arg("fd"), py::arg("kind"), py::arg("src"))
+      .def("recv", [](FdChannel& ch, int timeout_ms) -> py::object {
+        FdMessage m;
+        bool ok;
+        {
+          py::gil_scoped_release rel;
+          ok = ch.try_recv(&m, timeout_ms);
+        }
+        if (!ok) return py::none();
+        return py::make_tuple(m.fd, m.kind, m.src);
+      }, py::arg("timeout_ms"));
   py::class_<PreparedCodec>(m, "PreparedCodec")
       .def(py::init<const std::vector<LayerTuple>&, at::ScalarType, int64_t, bool>(), py::arg("layers"),
            py::arg("dtype"), py::arg("device") = 0, py::arg("skip_incomplete") = false)
@@ -550,6 +583,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
            py::arg("average") = false, py::arg("skip_incomplete") = false, py::arg("stochastic") = false,
            py::arg("seed") = 0, py::arg("seq") = 0)
       .def("check", &LocalSraGroup::check)
+      .def("allreduce_with_absent_rank", &LocalSraGroup::allreduce_with_absent_rank, py::arg("tensors"),
+           py::arg("layers"), py::arg("absent"))
+      .def("abort_all", &LocalSraGroup::abort_all)
+      .def("status", &LocalSraGroup::status)
+      .def("clear", &LocalSraGroup::clear)
       .def("lanes_used", &LocalSraGroup::lanes_used);
 
   m.attr("MAX_BLOCK_ELEMS") = (int64_t)kMaxBlockElems;

@@ -82,10 +82,13 @@ class SymmetricHeap {
   uint8_t* mc_oneshot(int parity) const { return mc_base_ ? mc_base_ + layout_.os_off[parity & 1] : nullptr; }
   DeviceSync* sync_device() const { return reinterpret_cast<DeviceSync*>(bases_[rank_] + layout_.sync_off); }
 
-  // host-visible error word written by kernels on timeout
+  // host-visible error word written by kernels on timeout (word 0) and the abort request the
+  // host raises to make every spinning kernel of this heap give up (word 1)
   uint32_t* status_device() const { return status_dev_; }
+  const uint32_t* abort_device() const { return status_dev_ + 1; }
   uint32_t status_host() const { return status_host_ ? *(volatile uint32_t*)status_host_ : 0; }
   void clear_status() { if (status_host_) *(volatile uint32_t*)status_host_ = 0; }
+  void request_abort(bool on) { if (status_host_) *((volatile uint32_t*)status_host_ + 1) = on ? 1u : 0u; }
 
  private:
   void alloc_cuda_malloc();

@@ -148,18 +148,22 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
-// Spin until *flag reaches `epoch` (wrap-safe). Returns false on timeout.
-__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch, uint64_t timeout_ns) {
+// Spin until *flag reaches `epoch` (wrap-safe). Returns 0 when it did, 1 on timeout, 2 when the
+// host asked every kernel of this heap to give up (`abort_word`, host-mapped memory, polled only
+// every 1024 spins: it costs a PCIe round trip).
+__device__ __forceinline__ int wait_flag(const uint32_t* flag, uint32_t epoch, uint64_t timeout_ns,
+                                         const uint32_t* abort_word) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
     if ((++spins & 0x3FFu) == 0) {
+      if (abort_word != nullptr && *reinterpret_cast<const volatile uint32_t*>(abort_word) != 0) return 2;
       uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > timeout_ns) return false;
+      else if (now - t0 > timeout_ns) return 1;
     }
   }
-  return true;
+  return 0;
 }
 
 }  // namespace dev

@@ -42,6 +42,7 @@ struct SraParams {
   uint8_t* mc_recv2;
   int mc_reduce;                 // raw items are reduced inside the switch (multimem.ld_reduce)
   uint32_t* status;              // local error word (0 = ok), host-mapped
+  const uint32_t* abort_word;    // host-mapped: non-zero = stop waiting for peers (ProcessGroup::abort)
   uint64_t timeout_ns;
   DeviceSync* sync;
   unsigned long long* trace;     // optional [lanes][8] device timestamps (ns, globaltimer), nullptr = off
@@ -53,7 +54,7 @@ struct SraParams {
 constexpr int kSraThreads = 256;
 constexpr int kSraWarps = kSraThreads / 32;
 constexpr int kSraCtasPerSm = 2;
-enum SraStatus : uint32_t { kSraOk = 0, kSraTimeoutPhase1 = 1, kSraTimeoutPhase2 = 2 };
+enum SraStatus : uint32_t { kSraOk = 0, kSraTimeoutPhase1 = 1, kSraTimeoutPhase2 = 2, kSraAborted = 3 };
 
 // max CTAs of the fused kernel that can be co-resident on the current device
 int sra_max_resident_ctas(int dtype);

@@ -66,16 +66,17 @@ __device__ __forceinline__ void signal_peers(uint32_t* const* flags, int W, int 
   if (wl < (uint32_t)W && (int)wl != r) st_release_sys(flags[wl] + (size_t)r * flag_stride + lane, epoch);
 }
 
-// warp 0: wait until every peer's flag for this lane reached the epoch. Returns false on timeout.
-__device__ __forceinline__ bool wait_peers(const uint32_t* my_flags, int W, int r, uint32_t flag_stride, int lane,
-                                           uint32_t epoch, uint64_t timeout_ns, uint32_t* status, uint32_t code) {
+// warp 0: wait until every peer's flag for this lane reached the epoch. Returns false on timeout
+// or abort (and records who was missing in the host-visible status word).
+__device__ __forceinline__ bool wait_peers(const uint32_t* my_flags, const SraParams& p, int lane, uint32_t epoch,
+                                           uint32_t code) {
   const uint32_t wl = lane_id();
-  bool ok = true;
-  if (wl < (uint32_t)W && (int)wl != r) {
-    ok = wait_flag(my_flags + (size_t)wl * flag_stride + lane, epoch, timeout_ns);
-    if (!ok) *status = code | (wl << 8) | ((uint32_t)lane << 16);
+  int rc = 0;
+  if (wl < (uint32_t)p.world && (int)wl != p.rank) {
+    rc = wait_flag(my_flags + (size_t)wl * p.flag_stride + lane, epoch, p.timeout_ns, p.abort_word);
+    if (rc != 0) *p.status = (rc == 2 ? (uint32_t)kSraAborted : code) | (wl << 8) | ((uint32_t)lane << 16);
   }
-  return __all_sync(kAll, ok);
+  return __all_sync(kAll, rc == 0);
 }
 
 // ---- per-lane item cache ----------------------------------------------------------------
@@ -223,8 +224,7 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
   // ------------------------------------------------------------------ phase B
   {
     if (warp == 0 && own_end > 0) {
-      if (!wait_peers(p.flags1[r], W, r, p.flag_stride, lane, epoch, p.timeout_ns, p.status, kSraTimeoutPhase1))
-        s_abort = 1;
+      if (!wait_peers(p.flags1[r], p, lane, epoch, kSraTimeoutPhase1)) s_abort = 1;
     }
     __syncthreads();
     trace_mark(p.trace, lane, 2);
@@ -286,9 +286,11 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
         if ((++spins & 0x3FFu) == 0) {
           const uint64_t now = globaltimer_ns();
           if (t0 == 0) t0 = now;
-          if (__any_sync(kAll, now - t0 > p.timeout_ns)) {
+          const bool aborted = *reinterpret_cast<const volatile uint32_t*>(p.abort_word) != 0;
+          if (__any_sync(kAll, aborted || now - t0 > p.timeout_ns)) {
             if (wl == (uint32_t)__ffs(pending) - 1u)
-              *p.status = kSraTimeoutPhase2 | ((uint32_t)((r + (int)wl) % W) << 8) | ((uint32_t)lane << 16);
+              *p.status = (aborted ? (uint32_t)kSraAborted : (uint32_t)kSraTimeoutPhase2) |
+                          ((uint32_t)((r + (int)wl) % W) << 8) | ((uint32_t)lane << 16);
             break;
           }
         }
@@ -421,8 +423,7 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
   // ---- phase 2: all W images (mine was written by this CTA, ordered by the bar.sync above)
   {
     if (warp == 0 && total > 0) {
-      if (!wait_peers(p.flags1[r], W, r, p.flag_stride, lane, epoch, p.timeout_ns, p.status, kSraTimeoutPhase1))
-        s_abort = 1;
+      if (!wait_peers(p.flags1[r], p, lane, epoch, kSraTimeoutPhase1)) s_abort = 1;
     }
     __syncthreads();
     trace_mark(p.trace, lane, 2);

@@ -37,18 +37,21 @@ class C10dKV : public KVStore {
 
 // ---------------------------------------------------------------- WorkCGX ---
 WorkCGX::WorkCGX(int rank, c10d::OpType op, const char* title, std::vector<at::Tensor> outputs,
-                 c10::Device device, c10::cuda::CUDAStream comm_stream)
+                 c10::Device device, c10::cuda::CUDAStream comm_stream, ProcessGroupCGX* owner)
     : c10d::Work(rank, op, title, std::optional<std::vector<at::Tensor>>(outputs)),
       outputs_(std::move(outputs)),
       device_(device),
       comm_stream_(comm_stream),
-      end_event_(cudaEventDisableTiming) {
+      end_event_(cudaEventDisableTiming),
+      start_event_(cudaEventDisableTiming),
+      owner_(owner) {
   future_ = c10::make_intrusive<c10::ivalue::Future>(c10::ListType::create(c10::TensorType::get()),
                                                      std::vector<c10::Device>{device_});
 }
 
 void WorkCGX::finish_on_stream() {
   end_event_.record(comm_stream_);
+  end_recorded_ = true;
   {
     // the Future records its own events on the *current* stream of its devices:
     // make that the comm stream so .then() callbacks / wait() order after the kernel
@@ -58,12 +61,37 @@ void WorkCGX::finish_on_stream() {
   finish();  // completed_ = true (the GPU work itself is tracked by end_event_)
 }
 
-bool WorkCGX::isCompleted() { return end_event_.query(); }
-bool WorkCGX::isSuccess() const { return true; }
-void WorkCGX::synchronize() { end_event_.block(c10::cuda::getCurrentCUDAStream(device_.index())); }
+void WorkCGX::fail_now(std::exception_ptr e) {
+  future_->setError(e);
+  finish(e);
+}
+
+void WorkCGX::set_error(std::exception_ptr e) {
+  std::lock_guard<std::mutex> g(mutex_);
+  if (!exception_) exception_ = e;
+}
+
+bool WorkCGX::isCompleted() { return !end_recorded_ || end_event_.query(); }
+
+void WorkCGX::synchronize() {
+  if (end_recorded_) end_event_.block(c10::cuda::getCurrentCUDAStream(device_.index()));
+}
+
 bool WorkCGX::wait(std::chrono::milliseconds /*timeout*/) {
-  // CUDA semantics of c10d: make the caller's current stream wait, never block the host
+  // CUDA semantics of c10d: make the caller's current stream wait, never block the host ...
   synchronize();
+  // ... unless asked to (CGX_BLOCKING_WAIT=1): then a device-side failure surfaces right here
+  if (end_recorded_ && owner_ != nullptr && owner_->blocking_wait()) {
+    end_event_.synchronize();
+    const std::string msg = owner_->poll_failure();
+    if (!msg.empty()) set_error(std::make_exception_ptr(std::runtime_error(msg)));
+  }
+  std::exception_ptr e;
+  {
+    std::lock_guard<std::mutex> g(mutex_);
+    e = exception_;
+  }
+  if (e) std::rethrow_exception(e);
   return true;
 }
 std::vector<at::Tensor> WorkCGX::result() { return outputs_; }
@@ -127,6 +155,7 @@ ProcessGroupCGX::ProcessGroupCGX(const c10::intrusive_ptr<c10d::Store>& store, i
       topo_(std::move(topo)),
       cfg_(EngineConfig::read()) {
   compress_cpu_ = env_bool("CGX_COMPRESS_CPU", false);
+  blocking_wait_ = env_bool("CGX_BLOCKING_WAIT", false);
   engine_ = std::make_unique<AllreduceEngine>(rank, size, cfg_);
   engine_->set_topology(topo_.local_size > 0 ? topo_.local_size : size);
   TORCH_CHECK(engine_->local_size() <= kMaxPeers || cfg_.inner_comm != CommType::kP2P,
@@ -149,6 +178,12 @@ ProcessGroupCGX::ProcessGroupCGX(const c10::intrusive_ptr<c10d::Store>& store, i
 }
 
 ProcessGroupCGX::~ProcessGroupCGX() {
+  {
+    std::lock_guard<std::mutex> g(fail_mu_);
+    watchdog_stop_ = true;
+  }
+  watchdog_cv_.notify_all();
+  if (watchdog_.joinable()) watchdog_.join();
   worker_.reset();  // finishes queued host jobs before the engine goes away
   if (engine_ && device_ >= 0) {
     c10::cuda::CUDAGuard g(device_);
@@ -189,7 +224,6 @@ void ProcessGroupCGX::ensure_cuda(c10::DeviceIndex dev) {
   c10::cuda::CUDAGuard g(dev);
   device_ = dev;
   comm_stream_ = c10::cuda::getStreamFromPool(/*isHighPriority=*/true, dev);
-  start_event_.emplace(cudaEventDisableTiming);
   const int lsize = engine_->local_size(), lrank = engine_->local_rank(), node = engine_->node();
 
   // device-memory generic reducers (NCCL send/recv transport): cross-node stage, intra-node
@@ -234,6 +268,70 @@ void ProcessGroupCGX::ensure_cuda(c10::DeviceIndex dev) {
             getRank(), (int)dev, node, lrank, lsize, lanes, (double)layout.total / (1 << 20), layout.slot_bytes);
   }
   cuda_ready_ = true;
+  if (engine_->has_p2p() && !watchdog_.joinable()) watchdog_ = std::thread([this] { watchdog_loop(); });
+}
+
+// ------------------------------------------------------------ failure detection ---
+std::string ProcessGroupCGX::failure() const {
+  std::lock_guard<std::mutex> g(fail_mu_);
+  return failure_;
+}
+
+std::string ProcessGroupCGX::poll_failure() {
+  {
+    std::lock_guard<std::mutex> g(fail_mu_);
+    if (!failure_.empty()) return failure_;
+  }
+  if (!engine_ || !engine_->has_p2p()) return std::string();
+  const std::string msg = engine_->fused()->status_message();  // reads host-mapped memory only
+  if (msg.empty()) return msg;
+  fail_inflight(msg);
+  return failure();
+}
+
+void ProcessGroupCGX::fail_inflight(const std::string& msg) {
+  std::deque<c10::weak_intrusive_ptr<WorkCGX>> works;
+  {
+    std::lock_guard<std::mutex> g(fail_mu_);
+    if (!failure_.empty()) return;
+    failure_ = msg;
+    works.swap(inflight_);
+  }
+  log_msg(0, "cgx[%d]: %s", getRank(), msg.c_str());
+  const std::exception_ptr e = std::make_exception_ptr(std::runtime_error(msg));
+  for (auto& w : works)
+    if (auto sp = w.lock()) sp->set_error(e);
+}
+
+void ProcessGroupCGX::watchdog_loop() {
+  std::unique_lock<std::mutex> lk(fail_mu_);
+  while (!watchdog_stop_) {
+    watchdog_cv_.wait_for(lk, std::chrono::milliseconds(50));
+    if (watchdog_stop_) break;
+    // forget works whose kernel has finished cleanly
+    while (!inflight_.empty()) {
+      auto sp = inflight_.front().lock();
+      if (sp && !sp->gpu_done()) break;
+      inflight_.pop_front();
+    }
+    if (!failure_.empty()) continue;
+    lk.unlock();
+    (void)poll_failure();
+    lk.lock();
+  }
+}
+
+void ProcessGroupCGX::abort() {
+  if (engine_ && engine_->heap()) engine_->heap()->request_abort(true);
+  fail_inflight("cgx: process group aborted on rank " + std::to_string(getRank()));
+  if (cuda_delegate_) cuda_delegate_->abort();
+  if (cpu_delegate_) cpu_delegate_->abort();
+}
+
+void ProcessGroupCGX::shutdown() {
+  if (worker_) worker_->drain();
+  if (cuda_delegate_) cuda_delegate_->shutdown();
+  if (cpu_delegate_) cpu_delegate_->shutdown();
 }
 
 c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::engine_allreduce(at::Tensor& t, bool average, int bucket_idx) {
@@ -242,18 +340,32 @@ c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::engine_allreduce(at::Tensor& t, 
   c10::cuda::CUDAGuard g(dev);
   auto cur = c10::cuda::getCurrentCUDAStream(dev);
   auto work = c10::make_intrusive<WorkCGX>(getRank(), c10d::OpType::ALLREDUCE, "cgx:all_reduce",
-                                           std::vector<at::Tensor>{t}, t.device(), *comm_stream_);
+                                           std::vector<at::Tensor>{t}, t.device(), *comm_stream_, this);
+  {
+    // a group that has failed (device timeout, abort) refuses new work: the error travels in the
+    // Work and in its Future (DDP raises it from backward) instead of hanging on dead peers
+    const std::string failed = poll_failure();
+    if (!failed.empty()) {
+      work->fail_now(std::make_exception_ptr(std::runtime_error(failed)));
+      return work;
+    }
+  }
   {
     std::lock_guard<std::mutex> lk(mu_);
     ++seq_;
     // order after the producer of `t` on the caller's stream
-    start_event_->record(cur);
-    start_event_->block(*comm_stream_);
+    work->start_event_.record(cur);
+    work->start_event_.block(*comm_stream_);
     // the caching allocator must not hand this memory out while the comm stream uses it
     c10::cuda::CUDACachingAllocator::recordStream(t.storage().data_ptr(), *comm_stream_);
     engine_->allreduce_cuda(t.data_ptr(), to_cgx_dtype(t.scalar_type()), t.numel(), average, bucket_idx,
                             comm_stream_->stream(), /*overlapped=*/bucket_idx >= 0);
     work->finish_on_stream();
+  }
+  if (engine_->has_p2p()) {
+    std::lock_guard<std::mutex> g2(fail_mu_);
+    inflight_.emplace_back(work);
+    if (inflight_.size() > 4096) inflight_.pop_front();
   }
   return work;
 }
@@ -425,7 +537,7 @@ c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::barrier(const c10d::BarrierOptio
   if (cuda_ready_ && device_ >= 0) {
     c10::cuda::CUDAGuard g(device_);
     comm_stream_->synchronize();
-    engine_->check_health();
+    check_health();
   }
   const bool use_cuda = cuda_delegate_ && (opts.device.has_value() ? opts.device->is_cuda() : device_ >= 0);
   if (use_cuda) return cuda_delegate_->barrier(opts);
@@ -462,7 +574,8 @@ at::Tensor ProcessGroupCGX::read_trace() {
 }
 
 void ProcessGroupCGX::check_health() {
-  if (engine_) engine_->check_health();
+  const std::string msg = poll_failure();
+  if (!msg.empty()) throw std::runtime_error(msg);
 }
 
 }  // namespace cgx

@@ -39,25 +39,43 @@
 
 namespace cgx {
 
+class ProcessGroupCGX;
+
+// Work of one engine allreduce. Like ProcessGroupNCCL it is "complete" for stream-ordering purposes
+// as soon as the kernel is enqueued (wait() makes the caller's stream wait on the end event, the
+// CUDA-aware Future carries the same event). Failures are asynchronous: when a fused kernel
+// reports a timeout / abort in the host-mapped status word, the backend's watchdog stores the
+// error in every Work still in flight (isSuccess() / exception() / wait() then report it) and
+// every later collective fails fast. With CGX_BLOCKING_WAIT=1, wait() blocks the host until the
+// kernel has finished and throws right there.
+// Reference: WorkMPI + finishWorkMPIError (/root/reference/src/ProcessGroupCGX.cc:120-142, :312-317).
 class WorkCGX : public c10d::Work {
  public:
   WorkCGX(int rank, c10d::OpType op, const char* title, std::vector<at::Tensor> outputs, c10::Device device,
-          c10::cuda::CUDAStream comm_stream);
+          c10::cuda::CUDAStream comm_stream, ProcessGroupCGX* owner);
   bool isCompleted() override;
-  bool isSuccess() const override;
   bool wait(std::chrono::milliseconds timeout = kNoTimeout) override;
   void synchronize() override;
   std::vector<at::Tensor> result() override;
   c10::intrusive_ptr<c10::ivalue::Future> getFuture() override;
   // record the end of the work on the comm stream and complete the future
   void finish_on_stream();
+  // the collective was refused (group already failed / aborted): Work and Future carry the error
+  void fail_now(std::exception_ptr e);
+  // the watchdog found a device-side failure while this Work was in flight
+  void set_error(std::exception_ptr e);
+  bool gpu_done() const { return end_recorded_ && end_event_.query(); }
 
  private:
   std::vector<at::Tensor> outputs_;
   c10::Device device_;
   c10::cuda::CUDAStream comm_stream_;
   at::cuda::CUDAEvent end_event_;
+  at::cuda::CUDAEvent start_event_;  // per Work: nothing shared between calls
+  bool end_recorded_ = false;
+  ProcessGroupCGX* owner_;
   c10::intrusive_ptr<c10::ivalue::Future> future_;
+  friend class ProcessGroupCGX;
 };
 
 // Delegates of the node-local and cross-node sub-groups (hierarchical allreduce);
@@ -149,6 +167,12 @@ class ProcessGroupCGX : public c10d::Backend {
   void setSequenceNumberForGroup() override {}
   uint64_t getSequenceNumberForGroup() override { return seq_; }
 
+  // Make every spinning kernel of this group give up, fail everything in flight and refuse new
+  // collectives (reference: ProcessGroupCGX::abort -> MPI_Abort, ProcessGroupCGX.cc:295-298; here
+  // the process survives and sees RuntimeErrors).
+  void abort() override;
+  void shutdown() override;
+
   // ---- cgx-specific API (bound to Python) ----------------------------------
   // allreduce of one DDP bucket whose index is known (no cursor guessing);
   // average == true fuses the 1/world scale into the kernel.
@@ -161,6 +185,15 @@ class ProcessGroupCGX : public c10d::Backend {
   std::vector<int64_t> stats() const;  // calls, kernel launches, elements, wire bytes, raw bytes
   void reset_stats();
   void check_health();
+  // empty when healthy, else the first failure this group has seen
+  std::string failure() const;
+  bool blocking_wait() const { return blocking_wait_; }
+  int64_t last_lanes() const { return engine_ && engine_->has_p2p() ? engine_->fused()->last_lanes() : 0; }
+  bool uses_multicast() const { return engine_ && engine_->has_p2p() && engine_->fused()->uses_multicast(); }
+  std::string heap_kind() const {
+    if (!engine_ || !engine_->heap()) return "none";
+    return engine_->heap()->kind() == HeapKind::kVmm ? "vmm" : "cudaMalloc";
+  }
   // per-lane device timestamps of the last fused allreduce (see FusedSra::read_trace)
   void enable_trace(bool on);
   at::Tensor read_trace();
@@ -182,11 +215,24 @@ class ProcessGroupCGX : public c10d::Backend {
   EngineConfig cfg_;
   std::unique_ptr<AllreduceEngine> engine_;
   std::optional<c10::cuda::CUDAStream> comm_stream_;
-  std::optional<at::cuda::CUDAEvent> start_event_;
   c10::DeviceIndex device_ = -1;
   std::mutex mu_;
   uint64_t seq_ = 0;
   std::unique_ptr<HostWorker> worker_;  // created on first use
+
+  // ---- failure detection -------------------------------------------------------------------
+  // returns the failure (recording it on first sight) or an empty string
+  std::string poll_failure();
+  void fail_inflight(const std::string& msg);
+  void watchdog_loop();
+  bool blocking_wait_ = false;
+  mutable std::mutex fail_mu_;
+  std::string failure_;                 // first failure seen (sticky)
+  std::deque<c10::weak_intrusive_ptr<WorkCGX>> inflight_;
+  std::thread watchdog_;
+  std::condition_variable watchdog_cv_;
+  bool watchdog_stop_ = false;
+  friend class WorkCGX;
 };
 
 }  // namespace cgx

@@ -148,6 +148,7 @@ void FusedSra::launch(const DevicePlan& dp, void* data, float prescale, const Rn
   p.mc_recv2 = (mc && !oneshot) ? heap_->mc_recv2() : nullptr;
   p.mc_reduce = (mc && !oneshot && use_mc_reduce_) ? 1 : 0;
   p.status = heap_->status_device();
+  p.abort_word = heap_->abort_device();
   p.timeout_ns = timeout_ns_;
   p.sync = heap_->sync_device();
   p.trace = nullptr;
@@ -172,6 +173,9 @@ std::string FusedSra::status_message() const {
   const uint32_t s = heap_->status_host();
   if (s == 0) return std::string();
   const uint32_t code = s & 0xFF, peer = (s >> 8) & 0xFF, lane = s >> 16;
+  if (code == kSraAborted)
+    return "cgx: fused allreduce kernel on rank " + std::to_string(rank()) + " was aborted while waiting for rank " +
+           std::to_string(peer) + " (lane " + std::to_string(lane) + ")";
   return "cgx: fused allreduce kernel timed out on rank " + std::to_string(rank()) + " waiting for rank " +
          std::to_string(peer) + " (phase " + std::to_string(code) + ", lane " + std::to_string(lane) +
          "); a peer died, is stuck, or issued collectives in a different order "
@@ -179,10 +183,15 @@ std::string FusedSra::status_message() const {
 }
 
 void FusedSra::check_status() {
+  // sticky: a heap whose kernel gave up is out of step with its peers (epochs, flags) and must
+  // not be reused; clear_status() exists for tests that inject faults on purpose
   const std::string msg = status_message();
-  if (msg.empty()) return;
+  if (!msg.empty()) throw std::runtime_error(msg);
+}
+
+void FusedSra::clear_status() {
   heap_->clear_status();
-  throw std::runtime_error(msg);
+  heap_->request_abort(false);
 }
 
 }  // namespace cgx

@@ -52,8 +52,9 @@ class FusedSra {
                                     cudaStream_t stream, int max_lanes = 0);
   void run_oneshot(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream);
 
-  // throws std::runtime_error if a kernel reported a timeout
+  // throws std::runtime_error if a kernel reported a timeout / abort (sticky)
   void check_status();
+  void clear_status();
   // same, without throwing: empty string when healthy (does not clear the status)
   std::string status_message() const;
   bool uses_multicast() const { return use_mc_; }
