@@ -47,6 +47,9 @@ def parse_args():
     p.add_argument("--layer-min-size", type=int, default=1024)
     p.add_argument("--stochastic", type=int, default=-1)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-nccl-arm", action="store_true", help="skip the same-run NCCL DDP yardstick")
+    p.add_argument("--no-allreduce", action="store_true", help="skip the allreduce micro-benchmark block (N > 1)")
+    p.add_argument("--no-selftest", action="store_true", help="skip the multi-rank correctness self-test (N > 1)")
     p.add_argument("--hook", default="native", choices=["native", "python"],
                    help="native: C++ comm hook on the DDP reducer (default); python: cgx_hook as in the reference")
     return p.parse_args()
@@ -69,6 +72,74 @@ def reference_unavailable():
     if ref.exists() and any(ref.glob("torch_cgx*.so")):
         why = "baseline/_ref has a build but it needs mpirun + CUDA-aware MPI at run time, not present on this image"
     print(json.dumps({"impl": "reference", "unavailable": why}))
+
+
+def allreduce_microbench(dev, rank, world, nccl_pg, native):
+    """Device-timed cgx {2,4,8,32}-bit allreduce vs ncclAllReduce at this N: back-to-back calls over
+    rotating buffers (> 2x L2 in total), CUDA events, max over ranks, clocks sampled meanwhile."""
+    import torch
+    import torch.distributed as dist
+
+    from torch_cgx_b200.utils.clocks import ClockSampler
+
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    saved = {k: os.environ.get(k) for k in ("CGX_COMPRESSION_QUANTIZATION_BITS", "CGX_COMPRESSION_BUCKET_SIZE")}
+    os.environ["CGX_COMPRESSION_BUCKET_SIZE"] = "512"
+
+    def timeit(fn, bufs, iters, warmup=3):
+        for i in range(warmup):
+            fn(bufs[i % len(bufs)])
+        torch.cuda.synchronize()
+        reps = []
+        for _ in range(3):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(iters):
+                fn(bufs[i % len(bufs)])
+            e1.record()
+            torch.cuda.synchronize()
+            reps.append(e0.elapsed_time(e1) * 1e3 / iters)
+        t = torch.tensor(reps, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return sorted(t.tolist())[1]
+
+    rows = []
+    try:
+        for mb in (1, 16, 64, 256):
+            nbytes = mb << 20
+            n = nbytes // 4
+            nbuf = max(2, min(16, (288 << 20) // nbytes + 1))
+            bufs = [torch.randn(n, device=dev) for _ in range(nbuf)]
+            iters = 20 if mb <= 64 else 6
+            row = {"mb": mb, "dtype": "float32"}
+            if nccl_pg is not None:
+                row["nccl_us"] = round(timeit(lambda x: dist.all_reduce(x, group=nccl_pg), bufs, iters), 2)
+            for bits in (2, 4, 8, 32):
+                os.environ["CGX_COMPRESSION_QUANTIZATION_BITS"] = str(bits)
+                for x in bufs:
+                    x.normal_()
+                native.reset_stats()
+                t = timeit(lambda x: dist.all_reduce(x), bufs, iters)
+                st = native.stats()
+                row[f"cgx_{bits}bit_us"] = round(t, 2)
+                row[f"cgx_{bits}bit_wire_gbs"] = round(st[3] / max(1, st[0]) / t / 1e3, 1)
+                if "nccl_us" in row:
+                    row[f"cgx_{bits}bit_vs_nccl"] = round(row["nccl_us"] / t, 3)
+            rows.append(row)
+            del bufs
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return {"rows": rows, "clocks": sampler.stop() if rank == 0 else None,
+            "timing": "CUDA events around back-to-back calls over rotating buffers (> 2x L2 in total), max over ranks, median of 3",
+            "wire_gbs": "packed bytes this rank pushed over NVLink per call / time (per direction; 770 GB/s measured peer-copy peak)"}
 
 
 def main():
@@ -132,18 +203,27 @@ def main():
     net = net.to(dev)
     if not is_lm:
         net = net.to(memory_format=torch.channels_last)
-    ddp = DDP(net, device_ids=[local_rank], gradient_as_bucket_view=True)
-    if args.backend == "cgx":
-        state = cgx.CGXState(None, layer_min_size=args.layer_min_size,
-                             compression_params={"bits": bits, "bucket_size": args.bucket_size})
-        if args.hook == "native":
-            cgx.register_cgx_hook(ddp, state)
-        else:
-            ddp.register_comm_hook(state, cgx.cgx_hook)
+    nccl_pg = None
+    if args.backend == "cgx" and not args.no_nccl_arm:
+        nccl_pg = dist.new_group(backend="nccl")  # same-run yardstick: stock NCCL DDP, no hook
+
+    def make_ddp(kind):
+        if kind == "nccl_arm":
+            return DDP(net, device_ids=[local_rank], gradient_as_bucket_view=True, process_group=nccl_pg)
+        d = DDP(net, device_ids=[local_rank], gradient_as_bucket_view=True)
+        if args.backend == "cgx":
+            state = cgx.CGXState(None, layer_min_size=args.layer_min_size,
+                                 compression_params={"bits": bits, "bucket_size": args.bucket_size})
+            if args.hook == "native":
+                cgx.register_cgx_hook(d, state)
+            else:
+                d.register_comm_hook(state, cgx.cgx_hook)
+        return d
+
     if is_lm:
-        opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4, fused=True)
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, fused=True)
     else:
-        opt = torch.optim.SGD(ddp.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+        opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
 
     # synthetic data of the named shape, in PINNED HOST memory (a few distinct batches, cycled)
     if is_lm:
@@ -152,6 +232,8 @@ def main():
     else:
         ds = SyntheticHostDataset.images(batch, 3, 224, 224, 1000, n_batches=4, seed=rank)
         samples_per_step = batch
+
+    ddp = None  # set per arm
 
     def step(x, y):
         opt.zero_grad(set_to_none=True)
@@ -174,13 +256,9 @@ def main():
 
     resident = [to_dev(ds[i]) for i in range(len(ds))]
     torch.cuda.synchronize()
-
-    # ---- warm-up (W >= 3: DDP rebuilds buckets after step 1, layers register at step 3)
     warm = max(args.warmup, 3)
-    for i in range(warm):
-        step(*resident[i % len(resident)])
-    torch.cuda.synchronize()
     native = cgx.get_backend() if args.backend == "cgx" else None
+    from torch_cgx_b200.utils.metrics import AsyncScalarReader
 
     def timed(run_one, k):
         dist.barrier()
@@ -203,38 +281,72 @@ def main():
         launches = native.stats()[1] if native is not None else 0
         return t[0].item(), t[1].item(), launches, last
 
+    def run_arm():
+        """warm-up + (1) device-timed steps on resident inputs + (2) end-to-end steps (H2D of every
+        batch from pinned memory, D2H of every loss) with the CURRENT `ddp`."""
+        # W >= 3: DDP rebuilds buckets after step 1, the hook registers layers at step 3
+        for i in range(warm):
+            step(*resident[i % len(resident)])
+        torch.cuda.synchronize()
+        ms_dev, _, launches, last_loss = timed(lambda i: step(*resident[i % len(resident)]), args.steps)
+        e2e = None
+        if not args.no_e2e:
+            pf = CudaPrefetcher(ds, dev, channels_last=not is_lm)
+            it = iter(pf)
+            for _ in range(2):
+                step(*next(it)).item()
+            torch.cuda.synchronize()
+            reader = AsyncScalarReader(dev, depth=2)
+
+            def one(i):
+                x, y = next(it)
+                # D2H read of the loss EVERY step (pinned buffer, read one step late so the host
+                # keeps enqueueing); the last values are drained inside the timed region below
+                reader.push(step(x, y))
+                if i == args.steps - 1:
+                    reader.drain()
+                return None
+            _, ms_wall, _, _ = timed(one, args.steps)
+            assert len(reader.values) == args.steps, (len(reader.values), args.steps)
+            e2e = {"value": round(samples_per_step * world * args.steps / (ms_wall / 1e3), 2), "unit": unit,
+                   "h2d_bytes_per_step": ds.bytes_per_batch(), "d2h_bytes_per_step": 4,
+                   "ms_per_step": round(ms_wall / args.steps, 3),
+                   "timing": "host wall clock around K steps incl. prefetch-stream H2D of every batch and a pinned D2H read of every step's loss (consumed one step late, drained before the clock stops), max over ranks"}
+        return ms_dev, launches, last_loss, e2e
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # (1) device-timed, inputs resident on the device
-    ms_dev, _, launches, last_loss = timed(lambda i: step(*resident[i % len(resident)]), args.steps)
-    # (2) end to end through the public API: pinned host batch -> (prefetch stream) -> step -> loss to host
-    e2e = None
-    if not args.no_e2e:
-        pf = CudaPrefetcher(ds, dev, channels_last=not is_lm)
-        it = iter(pf)
-        for _ in range(2):
-            step(*next(it)).item()
+
+    # ---- same-run yardstick: the identical model / step / data on stock NCCL DDP (no compression)
+    baseline = None
+    if nccl_pg is not None:
+        ddp = make_ddp("nccl_arm")
+        b_ms, _, _, b_e2e = run_arm()
+        baseline = {"what": "same run, same model/step/data: PyTorch DDP over stock NCCL (fp32 gradients, no hook)",
+                    "value": round(samples_per_step * world * args.steps / (b_ms / 1e3), 2), "unit": unit,
+                    "ms_per_step": round(b_ms / args.steps, 3), "e2e": b_e2e}
+        del ddp
         torch.cuda.synchronize()
-        from torch_cgx_b200.utils.metrics import AsyncScalarReader
 
-        reader = AsyncScalarReader(dev, depth=2)
-
-        def one(i):
-            x, y = next(it)
-            # D2H read of the loss EVERY step (pinned buffer, read one step late so the host
-            # keeps enqueueing); the last values are drained inside the timed region below
-            reader.push(step(x, y))
-            if i == args.steps - 1:
-                reader.drain()
-            return None
-        _, ms_wall, _, _ = timed(one, args.steps)
-        assert len(reader.values) == args.steps, (len(reader.values), args.steps)
-        e2e_value = samples_per_step * world * args.steps / (ms_wall / 1e3)
-        e2e = {"value": round(e2e_value, 2), "unit": unit, "h2d_bytes_per_step": ds.bytes_per_batch(),
-               "d2h_bytes_per_step": 4, "ms_per_step": round(ms_wall / args.steps, 3),
-               "timing": "host wall clock around K steps incl. prefetch-stream H2D of every batch and a pinned D2H read of every step's loss (consumed one step late, drained before the clock stops), max over ranks"}
+    # ---- the product arm
+    ddp = make_ddp("main")
+    ms_dev, launches, last_loss, e2e = run_arm()
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- allreduce micro-benchmark + correctness self-test at this N (the driver only runs
+    # bench.py on several GPUs, so the multi-GPU evidence has to be produced here)
+    allreduce_block, selftest_block = None, None
+    if args.backend == "cgx" and world > 1:
+        if not args.no_selftest:
+            import importlib.util
+
+            spec = importlib.util.spec_from_file_location("cgx_selftest", str(ROOT / "bench" / "selftest.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            selftest_block = mod.run_selftest(dev)
+        if not args.no_allreduce:
+            allreduce_block = allreduce_microbench(dev, rank, world, nccl_pg, native)
 
     value = samples_per_step * world * args.steps / (ms_dev / 1e3)
     if rank == 0:
@@ -249,7 +361,10 @@ def main():
             "ms_per_step": round(ms_dev / args.steps, 3),
             "higher_is_better": True,
             "scaling": "weak",
-            "vs_baseline": None,
+            "vs_baseline": round(value / baseline["value"], 4) if baseline else None,
+            "baseline": baseline,
+            "e2e_vs_baseline": (round(e2e["value"] / baseline["e2e"]["value"], 4)
+                                if baseline and e2e and baseline.get("e2e") else None),
             "dtype": "bf16",
             "data": "synthetic (random images/tokens of the named shape, random-init weights)",
             "impl": args.backend,
@@ -267,6 +382,10 @@ def main():
             "gpu_launches": int(launches),
             "e2e": e2e,
             "clocks": clocks,
+            "heap": native.heap_kind() if native is not None else None,
+            "nvls_multicast": native.uses_multicast() if native is not None else None,
+            "allreduce": allreduce_block,
+            "selftest": selftest_block,
             "final_loss": round(float(last_loss.detach()), 4) if last_loss is not None else None,
         }
         print(json.dumps(out), flush=True)
