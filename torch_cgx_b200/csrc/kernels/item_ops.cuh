@@ -230,12 +230,50 @@ __device__ __forceinline__ void slice_decode(const SliceWords<GPL>& w, int bits,
   }
 }
 
-// x += decode(source i) for every source of the set, in slot order, `kPeerBatch` loads in flight
+// x += decode(source i) for every source of the set, in slot order.
+// Common case (one bucket == the slice): ONE {unit, min} per source, so the words of up to 8
+// sources are in flight at once -- at W = 8 the whole reduction of an item is a single round trip
+// to L2/HBM instead of four dependent ones. Slices made of several small buckets keep a
+// per-row meta and go two sources at a time.
 template <int KB, int GPL>
 __device__ __forceinline__ void slice_accumulate(const SrcSet& ss, uint32_t meta_off, uint32_t pay_off, uint32_t lg,
                                                  int bits, float (&x)[GPL][8]) {
-  constexpr int kB = SliceCfg<GPL>::kPeerBatch;
   const int cnt = ss.n - (ss.skip >= 0 ? 1 : 0);
+  if (slice_single_bucket<GPL>(lg)) {
+    constexpr int kB = GPL == 4 ? 2 : 4;
+    for (int i0 = 0; i0 < cnt; i0 += kB) {
+      uint32_t lo[kB][GPL], hi[kB][GPL];
+      float un[kB], mi[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        // past the end: re-read the last source (unconditional loads keep the arrays in
+        // registers; the value is simply not added)
+        const int i = min(i0 + u, cnt - 1);
+        const int q = (ss.skip >= 0 && i >= ss.skip) ? i + 1 : i;
+        const uint8_t* rec = ss.base + (size_t)q * ss.stride;
+#pragma unroll
+        for (int k = 0; k < GPL; ++k)
+          load_word<KB>(rec + pay_off, (uint32_t)k * 32u + lane_id(), bits, lo[u][k], hi[u][k]);
+        const uint2 v = ld_sys_v2(rec + meta_off);
+        un[u] = __uint_as_float(v.x);
+        mi[u] = __uint_as_float(v.y);
+      }
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        if (i0 + u < cnt) {
+#pragma unroll
+          for (int k = 0; k < GPL; ++k) {
+            float qf[8];
+            unpack_magic<KB>(lo[u][k], hi[u][k], bits, qf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[k][j] = __fadd_rn(x[k][j], __fmaf_rn(un[u], qf[j], mi[u]));
+          }
+        }
+      }
+    }
+    return;
+  }
+  constexpr int kB = SliceCfg<GPL>::kPeerBatch;
   for (int i0 = 0; i0 < cnt; i0 += kB) {
     SliceWords<GPL> w[kB];
 #pragma unroll
@@ -304,6 +342,88 @@ __device__ __forceinline__ void full_recv_sum(const SrcSet& ss, const WarpItem& 
     for (int j = 0; j < 8; ++j) x[k][j] = 0.f;
   slice_accumulate<KB, GPL>(ss, it.meta_off, it.pay_off, lg, bits, x);
   slice_store<TO, GPL, VEC>(out, x);
+}
+
+// ---- two items at once ------------------------------------------------------------------
+// With 16 warps per SM the dependent chains of one item (min/max tree -> redux -> reciprocal ->
+// encode -> pack) leave the schedulers idle; two independent items in ONE basic block give the
+// compiler twice the instruction-level parallelism. Only the common case qualifies: both slices
+// are a single bucket, deterministic rounding, finite values. Returns false (nothing done) if not.
+template <int GPL>
+__device__ __forceinline__ void slice_meta_single(const float (&x)[GPL][8], int bits, BucketMeta& m, float& inv) {
+  float mn = CGX_INF_POS, mx = CGX_INF_NEG;
+#pragma unroll
+  for (int k = 0; k < GPL; ++k) minmax8(x[k], mn, mx);
+  warp_minmax(mn, mx);
+  m = make_meta(mn, mx, bits);
+  inv = inv_unit(m.unit);
+}
+
+template <int KB, int GPL, typename DST>
+__device__ __forceinline__ bool full_send_pair(float (&xa)[GPL][8], float (&xb)[GPL][8], const WarpItem& ita,
+                                               const WarpItem& itb, float prescale, const RngKey& rng,
+                                               const DST& dsa, const DST& dsb) {
+  if (rng.enabled || !slice_single_bucket<GPL>(item_lpb_log2(ita)) || !slice_single_bucket<GPL>(item_lpb_log2(itb)))
+    return false;
+  const int bits_a = KB ? KB : item_bits(ita), bits_b = KB ? KB : item_bits(itb);
+  slice_scale<GPL>(xa, prescale);
+  slice_scale<GPL>(xb, prescale);
+  BucketMeta ma, mb;
+  float ia, ib;
+  slice_meta_single<GPL>(xa, bits_a, ma, ia);
+  slice_meta_single<GPL>(xb, bits_b, mb, ib);
+  if (lane_id() == 0) {
+    dst_st_v2(dsa, ita.meta_off, __float_as_uint(ma.unit), __float_as_uint(ma.min));
+    dst_st_v2(dsb, itb.meta_off, __float_as_uint(mb.unit), __float_as_uint(mb.min));
+  }
+  const bool finite = __all_sync(kAll, fabsf(ma.unit) < CGX_INF_POS && fabsf(mb.unit) < CGX_INF_POS);
+  BucketMeta mav[GPL], mbv[GPL];
+  float iav[GPL], ibv[GPL];
+#pragma unroll
+  for (int k = 0; k < GPL; ++k) {
+    mav[k] = ma;
+    mbv[k] = mb;
+    iav[k] = ia;
+    ibv[k] = ib;
+  }
+  if (finite) {
+    // interleave by rows so that both items' chains are in flight together
+    const float maxa = (float)max_level(bits_a), maxb = (float)max_level(bits_b);
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) {
+      const uint32_t gi = (uint32_t)k * 32u + lane_id();
+      float ua[8], ub[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ua[j] = level_magic<false>(xa[k][j], ma.min, ia, 0.5f, maxa);
+        ub[j] = level_magic<false>(xb[k][j], mb.min, ib, 0.5f, maxb);
+      }
+      uint32_t loa, hia, lob, hib;
+      pack_magic<KB>(ua, bits_a, loa, hia);
+      pack_magic<KB>(ub, bits_b, lob, hib);
+      store_word<KB>(dsa, ita.pay_off, gi, bits_a, loa, hia);
+      store_word<KB>(dsb, itb.pay_off, gi, bits_b, lob, hib);
+    }
+  } else {
+    slice_encode_mode<float, KB, GPL, false, true, 1>(xa, mav, iav, bits_a, rng, ita.elem_off, dsa, ita.pay_off,
+                                                      (float*)nullptr);
+    slice_encode_mode<float, KB, GPL, false, true, 1>(xb, mbv, ibv, bits_b, rng, itb.elem_off, dsb, itb.pay_off,
+                                                      (float*)nullptr);
+  }
+  return true;
+}
+
+// decode two already fetched items (branch free: the two chains interleave)
+template <typename TO, int KB, int GPL>
+__device__ __forceinline__ void full_recv_pair(const SliceWords<GPL>& wa, const SliceWords<GPL>& wb,
+                                               const WarpItem& ita, const WarpItem& itb, TO* __restrict__ oa,
+                                               TO* __restrict__ ob) {
+  const int bits_a = KB ? KB : item_bits(ita), bits_b = KB ? KB : item_bits(itb);
+  float xa[GPL][8], xb[GPL][8];
+  slice_decode<KB, GPL, false>(wa, bits_a, xa);
+  slice_decode<KB, GPL, false>(wb, bits_b, xb);
+  slice_store<TO, GPL, true>(oa, xa);
+  slice_store<TO, GPL, true>(ob, xb);
 }
 
 // ---- the same for slices whose gradients are not vector aligned: out of line, scalar access ----

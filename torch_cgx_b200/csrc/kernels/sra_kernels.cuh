@@ -120,15 +120,13 @@ __device__ __forceinline__ WarpItem lane_item(const LaneItems& li, const SraPara
   return p.items[li.gfirst[s] + (i - li.pre[s])];
 }
 
-// Fetch item `i` of a flat range and, if it is a hot kind with vector-aligned gradients, issue
-// the loads of its values (they are consumed one loop iteration later: the data of the NEXT item
-// is in flight while the current one is processed). hot: 0 cold item (loads its own data),
-// 1 full slice, 2 full raw item. Plain scalars/arrays on purpose: a struct here ends up in
-// local memory.
+// Fetch item `i` of a flat range (cursor `s` = its chunk slot, only ever moves forward) and, if it
+// is a hot kind with vector-aligned gradients, issue the loads of its values.
+// hot: 0 cold item (loads its own data)  1 full slice  2 full raw item.
+// Plain scalars / arrays on purpose: a struct here ends up in local memory.
 template <typename T, int GPL>
-__device__ __forceinline__ void prefetch_values(const LaneItems& li, const SraParams& p, uint32_t i, uint32_t end,
-                                                bool want_raw, WarpItem& it, int& s, int& hot,
-                                                float (&x)[GPL][8]) {
+__device__ __forceinline__ void fetch_values(const LaneItems& li, const SraParams& p, uint32_t i, uint32_t end,
+                                             WarpItem& it, int& s, int& hot, float (&x)[GPL][8]) {
   hot = 0;
   if (i >= end) return;
   while (i >= li.pre[s + 1]) ++s;
@@ -139,15 +137,18 @@ __device__ __forceinline__ void prefetch_values(const LaneItems& li, const SraPa
   if (kind == kItemFull) {
     hot = 1;
     slice_load_vec<T, GPL>(src, x);
-  } else if (kind == kItemRaw && want_raw) {
+  } else if (kind == kItemRaw) {
     hot = 2;
     raw_load_vec<T, GPL>(src, x);
   }
 }
 
-#define CGX_COPY_SLICE(dst, src)                 \
-  _Pragma("unroll") for (int k_ = 0; k_ < GPL; ++k_) \
-      _Pragma("unroll") for (int j_ = 0; j_ < 8; ++j_)(dst)[k_][j_] = (src)[k_][j_]
+#define CGX_COPY_WORDS(dst, src)                           \
+  _Pragma("unroll") for (int k_ = 0; k_ < GPL; ++k_) {     \
+    (dst).lo[k_] = (src).lo[k_];                           \
+    (dst).hi[k_] = (src).hi[k_];                           \
+    (dst).pm[k_] = (src).pm[k_];                           \
+  }
 
 template <typename T, int KB, int GPL>
 __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const __grid_constant__ SraParams p) {
@@ -168,24 +169,16 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
   const uint32_t own_end = li.pre[1], total = li.pre[W];
 
   // ------------------------------------------------------------------ phase A
-  // my copy of every other chunk -> its owner (items of all destinations dealt round-robin to
-  // the warps); with the in-switch reduction the full raw items of ALL chunks are staged locally
+  // my copy of every other chunk -> its owner. The items of all destinations are dealt round-robin
+  // to the warps; each warp takes them two at a time (ILP) and pulls the pair after that towards L2.
+  // With the in-switch reduction the full raw items of ALL chunks (mine included) are staged locally.
   {
     rng.stream = (uint32_t)r * 2u;
     const uint32_t begin = p.mc_reduce ? 0u : own_end;
-    WarpItem it, itn;
-    int cs = p.mc_reduce ? 0 : 1, hot, hotn;
-    float x[GPL][8], xn[GPL][8];
-    uint32_t i = begin + warp;
-    prefetch_values<T, GPL>(li, p, i, total, true, it, cs, hot, x);
-    while (i < total) {
-      int csn = cs;
-      prefetch_values<T, GPL>(li, p, i + kSraWarps, total, true, itn, csn, hotn, xn);
+    auto one = [&](const WarpItem& it, int cs, int hot, float (&x)[GPL][8]) {
       const uint32_t kind = item_kind(it);
       const int dstp = (r + cs) % W;
       T* blk = data + it.elem_off;
-      const OneDst push{p.recv1[dstp] + (size_t)r * p.slot_bytes};
-      bool done = false;
       if (p.mc_reduce) {
         if (kind == kItemRaw) {
           const OneDst stage{p.recv2[r] + (size_t)dstp * p.slot_bytes};
@@ -193,28 +186,53 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
             raw_full_x<T, 0, GPL>(x, blk, it, p.prescale, no_src, stage);
           else
             raw_generic<T>(blk, it, p.prescale, no_src, stage, 0);
-          done = true;
-        } else if (cs == 0) {
-          done = true;  // my own chunk: nothing else to send
+          return;
+        }
+        if (cs == 0) return;  // my own chunk: nothing else to send
+      }
+      const OneDst push{p.recv1[dstp] + (size_t)r * p.slot_bytes};
+      if (hot == 1)
+        full_send_x<T, KB, GPL, false, true>(x, it, p.prescale, rng, push, (T*)nullptr);
+      else if (hot == 2)
+        raw_full_x<T, 0, GPL>(x, blk, it, p.prescale, no_src, push);
+      else if (kind == kItemFull)
+        full_send_unaligned<T, T, KB, GPL, false>(blk, it, p.prescale, rng, push, (T*)nullptr);
+      else if (kind == kItemBucket)
+        bucket_quantize<T, T>(blk, it, p.prescale, rng, no_src, push, (T*)nullptr);
+      else
+        raw_generic<T>(blk, it, p.prescale, no_src, push, 0);
+    };
+    int sa = p.mc_reduce ? 0 : 1;
+    for (uint32_t i = begin + warp; i < total; i += 2 * kSraWarps) {
+      WarpItem ita, itb;
+      int hota = 0, hotb = 0, sb;
+      float xa[GPL][8], xb[GPL][8];
+      fetch_values<T, GPL>(li, p, i, total, ita, sa, hota, xa);
+      sb = sa;
+      const bool has_b = i + kSraWarps < total;
+      fetch_values<T, GPL>(li, p, i + kSraWarps, total, itb, sb, hotb, xb);
+      {  // next pair -> L2
+        int sn = sb;
+#pragma unroll
+        for (int u = 2; u < 4; ++u) {
+          const uint32_t in = i + (uint32_t)u * kSraWarps;
+          if (in < total) {
+            while (in >= li.pre[sn + 1]) ++sn;
+            slice_prefetch_l2<T, GPL>(data + lane_item(li, p, in, sn).elem_off);
+          }
         }
       }
-      if (!done) {
-        if (hot == 1)
-          full_send_x<T, KB, GPL, false, true>(x, it, p.prescale, rng, push, (T*)nullptr);
-        else if (hot == 2)
-          raw_full_x<T, 0, GPL>(x, blk, it, p.prescale, no_src, push);
-        else if (kind == kItemFull)
-          full_send_unaligned<T, T, KB, GPL, false>(blk, it, p.prescale, rng, push, (T*)nullptr);
-        else if (kind == kItemBucket)
-          bucket_quantize<T, T>(blk, it, p.prescale, rng, no_src, push, (T*)nullptr);
-        else
-          raw_generic<T>(blk, it, p.prescale, no_src, push, 0);
+      bool done = false;
+      if (hota == 1 && hotb == 1 && !(p.mc_reduce && sa == 0)) {
+        const OneDst pa{p.recv1[(r + sa) % W] + (size_t)r * p.slot_bytes};
+        const OneDst pb{p.recv1[(r + sb) % W] + (size_t)r * p.slot_bytes};
+        done = full_send_pair<KB, GPL>(xa, xb, ita, itb, p.prescale, rng, pa, pb);
       }
-      it = itn;
-      cs = csn;
-      hot = hotn;
-      CGX_COPY_SLICE(x, xn);
-      i += kSraWarps;
+      if (!done) {
+        one(ita, sa, hota, xa);
+        if (has_b) one(itb, sb, hotb, xb);
+      }
+      sa = sb;
     }
     __syncthreads();
     if (warp == 0) signal_peers(p.flags1, W, r, p.flag_stride, lane, epoch);
@@ -306,25 +324,16 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
         const uint32_t end = li.pre[s + 1];
         const uint8_t* slot = p.recv2[r] + (size_t)q * p.slot_bytes;
         const SrcSet ss{slot, 0u, 1, -1};
-        // software pipeline: the packed words of the next item are in flight while this one decodes
-        uint32_t i = li.pre[s] + ((warp - rot) & (kSraWarps - 1));
-        WarpItem it, itn;
-        SliceWords<GPL> w, wn;
-        bool hot = false, hotn = false;
-        if (i < end) {
+        // two items per iteration (ILP), and the packed words of the NEXT two are in flight while
+        // these decode
+        auto fetch = [&](uint32_t i, WarpItem& it, SliceWords<GPL>& w) -> bool {
+          if (i >= end) return false;
           it = lane_item(li, p, i, s);
-          hot = item_kind(it) == kItemFull && group_aligned<T>(data + it.elem_off);
-          if (hot) slice_fetch<KB, GPL>(slot, it.meta_off, it.pay_off, item_lpb_log2(it), KB ? KB : item_bits(it), w);
-        }
-        while (i < end) {
-          const uint32_t in = i + kSraWarps;
-          hotn = false;
-          if (in < end) {
-            itn = lane_item(li, p, in, s);
-            hotn = item_kind(itn) == kItemFull && group_aligned<T>(data + itn.elem_off);
-            if (hotn)
-              slice_fetch<KB, GPL>(slot, itn.meta_off, itn.pay_off, item_lpb_log2(itn), KB ? KB : item_bits(itn), wn);
-          }
+          const bool h = item_kind(it) == kItemFull && group_aligned<T>(data + it.elem_off);
+          if (h) slice_fetch<KB, GPL>(slot, it.meta_off, it.pay_off, item_lpb_log2(it), KB ? KB : item_bits(it), w);
+          return h;
+        };
+        auto one = [&](const WarpItem& it, const SliceWords<GPL>& w, bool hot) {
           const uint32_t kind = item_kind(it);
           T* blk = data + it.elem_off;
           if (hot) {
@@ -339,14 +348,26 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
           } else {
             raw_generic<T>(blk, it, 1.0f, ss, none, 2);
           }
-          it = itn;
-#pragma unroll
-          for (int k = 0; k < GPL; ++k) {
-            w.lo[k] = wn.lo[k];
-            w.hi[k] = wn.hi[k];
-            w.pm[k] = wn.pm[k];
+        };
+        uint32_t i = li.pre[s] + ((warp - rot) & (kSraWarps - 1));
+        WarpItem ita, itb, na, nb;
+        SliceWords<GPL> wa, wb, wna, wnb;
+        bool hota = fetch(i, ita, wa), hotb = fetch(i + kSraWarps, itb, wb);
+        while (i < end) {
+          const uint32_t in = i + 2 * kSraWarps;
+          const bool hna = fetch(in, na, wna), hnb = fetch(in + kSraWarps, nb, wnb);
+          if (hota && hotb) {
+            full_recv_pair<T, KB, GPL>(wa, wb, ita, itb, data + ita.elem_off, data + itb.elem_off);
+          } else {
+            one(ita, wa, hota);
+            if (i + kSraWarps < end) one(itb, wb, hotb);
           }
-          hot = hotn;
+          ita = na;
+          itb = nb;
+          CGX_COPY_WORDS(wa, wna);
+          CGX_COPY_WORDS(wb, wnb);
+          hota = hna;
+          hotb = hnb;
           i = in;
         }
       }
@@ -391,13 +412,12 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
     // additionally written with a plain local store so that phase 2 never depends on the loopback
     const MultiDst ds{p.recv1, p.mc_recv1, region + (uint32_t)r * p.slot_bytes, W, p.mc_recv1 ? r : -1,
                       p.mc_recv1 ? p.recv1[r] : nullptr};
-    WarpItem it, itn;
-    int cs = 0, csn = 0, hot, hotn;
-    float x[GPL][8], xn[GPL][8];
-    uint32_t i = warp;
-    prefetch_values<T, GPL>(li, p, i, total, true, it, cs, hot, x);
-    while (i < total) {
-      prefetch_values<T, GPL>(li, p, i + kSraWarps, total, true, itn, csn, hotn, xn);
+    for (uint32_t i = warp; i < total; i += kSraWarps) {
+      WarpItem it;
+      int cs = 0, hot = 0;
+      float x[GPL][8];
+      fetch_values<T, GPL>(li, p, i, total, it, cs, hot, x);
+      if (i + kSraWarps < total) slice_prefetch_l2<T, GPL>(data + lane_item(li, p, i + kSraWarps, 0).elem_off);
       const uint32_t kind = item_kind(it);
       T* blk = data + it.elem_off;
       if (hot == 1)
@@ -410,10 +430,6 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
         bucket_quantize<T, T>(blk, it, p.prescale, rng, no_src, ds, (T*)nullptr);
       else
         raw_generic<T>(blk, it, p.prescale, no_src, ds, 0);
-      it = itn;
-      hot = hotn;
-      CGX_COPY_SLICE(x, xn);
-      i += kSraWarps;
     }
     __syncthreads();
     if (warp == 0) signal_peers(p.flags1, W, r, p.flag_stride, lane, epoch);
