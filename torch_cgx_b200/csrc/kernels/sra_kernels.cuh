@@ -35,7 +35,8 @@ namespace dev {
 
 // Tracing: per-lane phase timestamps (slot 0: kernel start [min], 1: phase A done,
 // 2: phase B inputs arrived, 3: phase B done, 4: last phase-C wait satisfied, 5: end [max]).
-__device__ __forceinline__ void trace_mark(unsigned long long* trace, int lane, int slot, bool is_min = false) {
+__device__ __forceinline__ void trace_mark(const SraParams& p, int lane, int slot, bool is_min = false) {
+  unsigned long long* trace = p.trace;
   if (trace == nullptr || (threadIdx.x & 31u) != 0) return;
   const unsigned long long t = globaltimer_ns();
   if (is_min)
@@ -150,231 +151,252 @@ __device__ __forceinline__ void fetch_values(const LaneItems& li, const SraParam
     (dst).pm[k_] = (src).pm[k_];                           \
   }
 
+// Each phase is its own out-of-line function: ptxas allocates registers per function, so the
+// phase that needs most (B: the words of several sources in flight) does not push the streaming
+// phases (A, C: two items at a time) into spilling, and vice versa. Everything a phase needs is
+// re-derived from the parameter bank and the shared item cache.
+__device__ __forceinline__ RngKey phase_rng(const SraParams& p, uint32_t epoch, uint32_t phase) {
+  RngKey rng = p.rng;
+  rng.seq += epoch - p.epoch_hint;  // graph replays advance the random stream
+  rng.stream = (uint32_t)p.rank * 2u + phase;
+  return rng;
+}
+
+// ---- phase A: my copy of every other chunk -> its owner. The items of all destinations are dealt
+// round-robin to the warps; each warp takes them two at a time (ILP) and pulls the pair after that
+// towards L2. With the in-switch reduction the full raw items of ALL chunks (mine included) are
+// staged locally.
+template <typename T, int KB, int GPL>
+__device__ __forceinline__ void sra_phase_a(const SraParams& p, const LaneItems& li, uint32_t epoch) {
+  const int r = p.rank, W = p.world;
+  const uint32_t warp = threadIdx.x >> 5;
+  T* data = reinterpret_cast<T*>(p.data);
+  const RngKey rng = phase_rng(p, epoch, 0u);
+  const SrcSet no_src{nullptr, 0u, 0, -1};
+  const uint32_t own_end = li.pre[1], total = li.pre[W];
+  const uint32_t begin = p.mc_reduce ? 0u : own_end;
+  auto one = [&](const WarpItem& it, int cs, int hot, float (&x)[GPL][8]) {
+    const uint32_t kind = item_kind(it);
+    const int dstp = (r + cs) % W;
+    T* blk = data + it.elem_off;
+    if (p.mc_reduce) {
+      if (kind == kItemRaw) {
+        const OneDst stage{p.recv2[r] + (size_t)dstp * p.slot_bytes};
+        if (hot == 2)
+          raw_full_x<T, 0, GPL>(x, blk, it, p.prescale, no_src, stage);
+        else
+          raw_generic<T>(blk, it, p.prescale, no_src, stage, 0);
+        return;
+      }
+      if (cs == 0) return;  // my own chunk: nothing else to send
+    }
+    const OneDst push{p.recv1[dstp] + (size_t)r * p.slot_bytes};
+    if (hot == 1)
+      full_send_x<T, KB, GPL, false, true>(x, it, p.prescale, rng, push, (T*)nullptr);
+    else if (hot == 2)
+      raw_full_x<T, 0, GPL>(x, blk, it, p.prescale, no_src, push);
+    else if (kind == kItemFull)
+      full_send_unaligned<T, T, KB, GPL, false>(blk, it, p.prescale, rng, push, (T*)nullptr);
+    else if (kind == kItemBucket)
+      bucket_quantize<T, T>(blk, it, p.prescale, rng, no_src, push, (T*)nullptr);
+    else
+      raw_generic<T>(blk, it, p.prescale, no_src, push, 0);
+  };
+  int sa = p.mc_reduce ? 0 : 1;
+  for (uint32_t i = begin + warp; i < total; i += 2 * kSraWarps) {
+    WarpItem ita, itb;
+    int hota = 0, hotb = 0, sb;
+    float xa[GPL][8], xb[GPL][8];
+    fetch_values<T, GPL>(li, p, i, total, ita, sa, hota, xa);
+    sb = sa;
+    const bool has_b = i + kSraWarps < total;
+    fetch_values<T, GPL>(li, p, i + kSraWarps, total, itb, sb, hotb, xb);
+    {  // next pair -> L2
+      int sn = sb;
+#pragma unroll
+      for (int u = 2; u < 4; ++u) {
+        const uint32_t in = i + (uint32_t)u * kSraWarps;
+        if (in < total) {
+          while (in >= li.pre[sn + 1]) ++sn;
+          slice_prefetch_l2<T, GPL>(data + lane_item(li, p, in, sn).elem_off);
+        }
+      }
+    }
+    bool done = false;
+    if (hota == 1 && hotb == 1 && !(p.mc_reduce && sa == 0)) {
+      const OneDst pa{p.recv1[(r + sa) % W] + (size_t)r * p.slot_bytes};
+      const OneDst pb{p.recv1[(r + sb) % W] + (size_t)r * p.slot_bytes};
+      done = full_send_pair<KB, GPL>(xa, xb, ita, itb, p.prescale, rng, pa, pb);
+    }
+    if (!done) {
+      one(ita, sa, hota, xa);
+      if (has_b) one(itb, sb, hotb, xb);
+    }
+    sa = sb;
+  }
+}
+
+// ---- phase B: reduce my chunk. The registers of this phase belong to the sources' words (four
+// sources in flight); the NEXT item's own values are only pulled towards L2.
+template <typename T, int KB, int GPL>
+__device__ __forceinline__ void sra_phase_b(const SraParams& p, const LaneItems& li, uint32_t epoch) {
+  const int r = p.rank, W = p.world;
+  const uint32_t warp = threadIdx.x >> 5;
+  T* data = reinterpret_cast<T*>(p.data);
+  const RngKey rng = phase_rng(p, epoch, 1u);
+  const uint32_t own_end = li.pre[1];
+  const SrcSet ss{p.recv1[r], p.slot_bytes, W, r};
+  const MultiDst ds{p.recv2, p.mc_recv2, (uint32_t)r * p.slot_bytes, W, r, nullptr};
+  for (uint32_t i = warp; i < own_end; i += kSraWarps) {
+    const WarpItem it = lane_item(li, p, i, 0);
+    const uint32_t kind = item_kind(it);
+    T* blk = data + it.elem_off;
+    const bool al = group_aligned<T>(blk);
+    float x[GPL][8];
+    if (al && kind == kItemFull) slice_load_vec<T, GPL>(blk, x);
+    if (al && kind == kItemRaw && !p.mc_reduce) raw_load_vec<T, GPL>(blk, x);
+    if (i + kSraWarps < own_end) {
+      const WarpItem itn = lane_item(li, p, i + kSraWarps, 0);
+      if (!(p.mc_reduce && item_kind(itn) == kItemRaw)) slice_prefetch_l2<T, GPL>(data + itn.elem_off);
+    }
+    if (kind == kItemFull) {
+      if (al)
+        full_reduce_x<T, KB, GPL, true>(x, blk, it, p.prescale, rng, ss, ds);
+      else
+        full_reduce_unaligned<T, KB, GPL>(blk, it, p.prescale, rng, ss, ds);
+    } else if (kind == kItemBucket) {
+      bucket_quantize<T, T>(blk, it, p.prescale, rng, ss, ds, blk);
+    } else if (kind == kItemRaw && p.mc_reduce) {
+      raw_full_mc_reduce<T>(blk, it, p.mc_recv2 + (size_t)r * p.slot_bytes);
+    } else if (kind == kItemRaw && al) {
+      raw_full_x<T, 1, GPL>(x, blk, it, p.prescale, ss, ds);
+    } else {
+      raw_generic<T>(blk, it, p.prescale, ss, ds, 1);
+    }
+  }
+}
+
+// ---- phase C: decode every peer's reduced chunk, in order of arrival. Lane s of every warp looks
+// after chunk slot s (polls its flag); rot keeps the round-robin over warps continuous across
+// chunks. Two items per iteration (ILP) with the packed words of the NEXT two already in flight.
+template <typename T, int KB, int GPL>
+__device__ __forceinline__ void sra_phase_c(const SraParams& p, const LaneItems& li, uint32_t epoch) {
+  const int lane = blockIdx.x;
+  const int r = p.rank, W = p.world;
+  const uint32_t warp = threadIdx.x >> 5, wl = threadIdx.x & 31u;
+  T* data = reinterpret_cast<T*>(p.data);
+  const uint32_t own_end = li.pre[1];
+  const bool mine = wl >= 1 && wl < (uint32_t)W;
+  const uint32_t my_cnt = mine ? li.pre[wl + 1] - li.pre[wl] : 0u;
+  const uint32_t my_rot = mine ? li.pre[wl] - own_end : 0u;
+  const uint32_t* my_flag = p.flags2[r] + (size_t)((r + (int)wl) % W) * p.flag_stride + lane;
+  uint32_t pending = __ballot_sync(kAll, my_cnt > 0);
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  const OneDst none{nullptr};
+  while (pending) {
+    const bool rdy = ((pending >> wl) & 1u) && (int32_t)(ld_acquire_sys(my_flag) - epoch) >= 0;
+    uint32_t ready = __ballot_sync(kAll, rdy);
+    if (!ready) {
+      if ((++spins & 0x3FFu) == 0) {
+        const uint64_t now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        const bool aborted = *reinterpret_cast<const volatile uint32_t*>(p.abort_word) != 0;
+        if (__any_sync(kAll, aborted || now - t0 > p.timeout_ns)) {
+          if (wl == (uint32_t)__ffs(pending) - 1u)
+            *p.status = (aborted ? (uint32_t)kSraAborted : (uint32_t)kSraTimeoutPhase2) |
+                        ((uint32_t)((r + (int)wl) % W) << 8) | ((uint32_t)lane << 16);
+          break;
+        }
+      }
+      continue;
+    }
+    pending &= ~ready;
+    trace_mark(p, lane, 4);
+    while (ready) {
+      const int s = __ffs(ready) - 1;
+      ready &= ready - 1;
+      const int q = (r + s) % W;
+      const uint32_t rot = __shfl_sync(kAll, my_rot, s);
+      const uint32_t end = li.pre[s + 1];
+      const uint8_t* slot = p.recv2[r] + (size_t)q * p.slot_bytes;
+      const SrcSet ss{slot, 0u, 1, -1};
+      auto fetch = [&](uint32_t i, WarpItem& it, SliceWords<GPL>& w) -> bool {
+        if (i >= end) return false;
+        it = lane_item(li, p, i, s);
+        const bool h = item_kind(it) == kItemFull && group_aligned<T>(data + it.elem_off);
+        if (h) slice_fetch<KB, GPL>(slot, it.meta_off, it.pay_off, item_lpb_log2(it), KB ? KB : item_bits(it), w);
+        return h;
+      };
+      auto one = [&](const WarpItem& it, const SliceWords<GPL>& w, bool hot) {
+        const uint32_t kind = item_kind(it);
+        T* blk = data + it.elem_off;
+        if (hot) {
+          full_recv_w<T, KB, GPL, true>(w, it, blk);
+        } else if (kind == kItemFull) {
+          full_recv_unaligned<T, KB, GPL>(ss, it, blk);
+        } else if (kind == kItemRaw && group_aligned<T>(blk)) {
+          float x[2][8];
+          raw_full_x<T, 2, 2>(x, blk, it, 1.0f, ss, none);
+        } else if (kind == kItemBucket) {
+          bucket_recv<T>(ss, it, blk);
+        } else {
+          raw_generic<T>(blk, it, 1.0f, ss, none, 2);
+        }
+      };
+      uint32_t i = li.pre[s] + ((warp - rot) & (kSraWarps - 1));
+      WarpItem ita, itb, na, nb;
+      SliceWords<GPL> wa, wb, wna, wnb;
+      bool hota = fetch(i, ita, wa), hotb = fetch(i + kSraWarps, itb, wb);
+      while (i < end) {
+        const uint32_t in = i + 2 * kSraWarps;
+        const bool hna = fetch(in, na, wna), hnb = fetch(in + kSraWarps, nb, wnb);
+        if (hota && hotb) {
+          full_recv_pair<T, KB, GPL>(wa, wb, ita, itb, data + ita.elem_off, data + itb.elem_off);
+        } else {
+          one(ita, wa, hota);
+          if (i + kSraWarps < end) one(itb, wb, hotb);
+        }
+        ita = na;
+        itb = nb;
+        CGX_COPY_WORDS(wa, wna);
+        CGX_COPY_WORDS(wb, wnb);
+        hota = hna;
+        hotb = hnb;
+        i = in;
+      }
+    }
+  }
+}
+
 template <typename T, int KB, int GPL>
 __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const __grid_constant__ SraParams p) {
   __shared__ LaneItems li;
   __shared__ int s_abort;
   const int lane = blockIdx.x;
-  const int r = p.rank, W = p.world, G = p.lanes;
-  const uint32_t warp = threadIdx.x >> 5, wl = threadIdx.x & 31u;
-  T* data = reinterpret_cast<T*>(p.data);
   const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(&p.sync->epoch) + 1u;
-  RngKey rng = p.rng;
-  rng.seq += epoch - p.epoch_hint;  // graph replays advance the random stream
   if (threadIdx.x == 0) s_abort = 0;
-  lane_items_load(li, p, W);
-  trace_mark(p.trace, lane, 0, true);
+  lane_items_load(li, p, p.world);
+  trace_mark(p, lane, 0, true);
 
-  const SrcSet no_src{nullptr, 0u, 0, -1};
-  const uint32_t own_end = li.pre[1], total = li.pre[W];
+  sra_phase_a<T, KB, GPL>(p, li, epoch);
+  __syncthreads();
+  if (threadIdx.x < 32) signal_peers(p.flags1, p.world, p.rank, p.flag_stride, lane, epoch);
+  trace_mark(p, lane, 1);
 
-  // ------------------------------------------------------------------ phase A
-  // my copy of every other chunk -> its owner. The items of all destinations are dealt round-robin
-  // to the warps; each warp takes them two at a time (ILP) and pulls the pair after that towards L2.
-  // With the in-switch reduction the full raw items of ALL chunks (mine included) are staged locally.
-  {
-    rng.stream = (uint32_t)r * 2u;
-    const uint32_t begin = p.mc_reduce ? 0u : own_end;
-    auto one = [&](const WarpItem& it, int cs, int hot, float (&x)[GPL][8]) {
-      const uint32_t kind = item_kind(it);
-      const int dstp = (r + cs) % W;
-      T* blk = data + it.elem_off;
-      if (p.mc_reduce) {
-        if (kind == kItemRaw) {
-          const OneDst stage{p.recv2[r] + (size_t)dstp * p.slot_bytes};
-          if (hot == 2)
-            raw_full_x<T, 0, GPL>(x, blk, it, p.prescale, no_src, stage);
-          else
-            raw_generic<T>(blk, it, p.prescale, no_src, stage, 0);
-          return;
-        }
-        if (cs == 0) return;  // my own chunk: nothing else to send
-      }
-      const OneDst push{p.recv1[dstp] + (size_t)r * p.slot_bytes};
-      if (hot == 1)
-        full_send_x<T, KB, GPL, false, true>(x, it, p.prescale, rng, push, (T*)nullptr);
-      else if (hot == 2)
-        raw_full_x<T, 0, GPL>(x, blk, it, p.prescale, no_src, push);
-      else if (kind == kItemFull)
-        full_send_unaligned<T, T, KB, GPL, false>(blk, it, p.prescale, rng, push, (T*)nullptr);
-      else if (kind == kItemBucket)
-        bucket_quantize<T, T>(blk, it, p.prescale, rng, no_src, push, (T*)nullptr);
-      else
-        raw_generic<T>(blk, it, p.prescale, no_src, push, 0);
-    };
-    int sa = p.mc_reduce ? 0 : 1;
-    for (uint32_t i = begin + warp; i < total; i += 2 * kSraWarps) {
-      WarpItem ita, itb;
-      int hota = 0, hotb = 0, sb;
-      float xa[GPL][8], xb[GPL][8];
-      fetch_values<T, GPL>(li, p, i, total, ita, sa, hota, xa);
-      sb = sa;
-      const bool has_b = i + kSraWarps < total;
-      fetch_values<T, GPL>(li, p, i + kSraWarps, total, itb, sb, hotb, xb);
-      {  // next pair -> L2
-        int sn = sb;
-#pragma unroll
-        for (int u = 2; u < 4; ++u) {
-          const uint32_t in = i + (uint32_t)u * kSraWarps;
-          if (in < total) {
-            while (in >= li.pre[sn + 1]) ++sn;
-            slice_prefetch_l2<T, GPL>(data + lane_item(li, p, in, sn).elem_off);
-          }
-        }
-      }
-      bool done = false;
-      if (hota == 1 && hotb == 1 && !(p.mc_reduce && sa == 0)) {
-        const OneDst pa{p.recv1[(r + sa) % W] + (size_t)r * p.slot_bytes};
-        const OneDst pb{p.recv1[(r + sb) % W] + (size_t)r * p.slot_bytes};
-        done = full_send_pair<KB, GPL>(xa, xb, ita, itb, p.prescale, rng, pa, pb);
-      }
-      if (!done) {
-        one(ita, sa, hota, xa);
-        if (has_b) one(itb, sb, hotb, xb);
-      }
-      sa = sb;
-    }
-    __syncthreads();
-    if (warp == 0) signal_peers(p.flags1, W, r, p.flag_stride, lane, epoch);
+  if (threadIdx.x < 32 && li.pre[1] > 0) {
+    if (!wait_peers(p.flags1[p.rank], p, lane, epoch, kSraTimeoutPhase1)) s_abort = 1;
   }
-  trace_mark(p.trace, lane, 1);
+  __syncthreads();
+  trace_mark(p, lane, 2);
+  if (!s_abort) sra_phase_b<T, KB, GPL>(p, li, epoch);
+  __syncthreads();
+  if (threadIdx.x < 32 && !s_abort) signal_peers(p.flags2, p.world, p.rank, p.flag_stride, lane, epoch);
+  trace_mark(p, lane, 3);
 
-  // ------------------------------------------------------------------ phase B
-  {
-    if (warp == 0 && own_end > 0) {
-      if (!wait_peers(p.flags1[r], p, lane, epoch, kSraTimeoutPhase1)) s_abort = 1;
-    }
-    __syncthreads();
-    trace_mark(p.trace, lane, 2);
-    if (!s_abort) {
-      rng.stream = (uint32_t)r * 2u + 1u;
-      const SrcSet ss{p.recv1[r], p.slot_bytes, W, r};
-      const MultiDst ds{p.recv2, p.mc_recv2, (uint32_t)r * p.slot_bytes, W, r, nullptr};
-      // the registers of this phase belong to the peers' words: the NEXT item's own values are only
-      // pulled towards L2 (prefetch.global.L2), the current item's are loaded at the top
-      for (uint32_t i = warp; i < own_end; i += kSraWarps) {
-        const WarpItem it = lane_item(li, p, i, 0);
-        const uint32_t kind = item_kind(it);
-        T* blk = data + it.elem_off;
-        const bool al = group_aligned<T>(blk);
-        float x[GPL][8];
-        if (al && kind == kItemFull) slice_load_vec<T, GPL>(blk, x);
-        if (al && kind == kItemRaw && !p.mc_reduce) raw_load_vec<T, GPL>(blk, x);
-        if (i + kSraWarps < own_end) {
-          const WarpItem itn = lane_item(li, p, i + kSraWarps, 0);
-          if (!(p.mc_reduce && item_kind(itn) == kItemRaw)) slice_prefetch_l2<T, GPL>(data + itn.elem_off);
-        }
-        if (kind == kItemFull) {
-          if (al)
-            full_reduce_x<T, KB, GPL, true>(x, blk, it, p.prescale, rng, ss, ds);
-          else
-            full_reduce_unaligned<T, KB, GPL>(blk, it, p.prescale, rng, ss, ds);
-        } else if (kind == kItemBucket) {
-          bucket_quantize<T, T>(blk, it, p.prescale, rng, ss, ds, blk);
-        } else if (kind == kItemRaw && p.mc_reduce) {
-          raw_full_mc_reduce<T>(blk, it, p.mc_recv2 + (size_t)r * p.slot_bytes);
-        } else if (kind == kItemRaw && al) {
-          raw_full_x<T, 1, GPL>(x, blk, it, p.prescale, ss, ds);
-        } else {
-          raw_generic<T>(blk, it, p.prescale, ss, ds, 1);
-        }
-      }
-    }
-    __syncthreads();
-    if (warp == 0 && !s_abort) signal_peers(p.flags2, W, r, p.flag_stride, lane, epoch);
-  }
-  trace_mark(p.trace, lane, 3);
-
-  // ------------------------------------------------------------------ phase C
-  if (!s_abort) {
-    // lane s of every warp looks after chunk slot s: polls its flag; chunks are decoded in
-    // order of arrival. rot keeps the round-robin over warps continuous across chunks.
-    const bool mine = wl >= 1 && wl < (uint32_t)W;
-    const uint32_t my_cnt = mine ? li.pre[wl + 1] - li.pre[wl] : 0u;
-    const uint32_t my_rot = mine ? li.pre[wl] - own_end : 0u;
-    const uint32_t* my_flag = p.flags2[r] + (size_t)((r + (int)wl) % W) * p.flag_stride + lane;
-    uint32_t pending = __ballot_sync(kAll, my_cnt > 0);
-    uint32_t spins = 0;
-    uint64_t t0 = 0;
-    const OneDst none{nullptr};
-    while (pending) {
-      const bool rdy = ((pending >> wl) & 1u) && (int32_t)(ld_acquire_sys(my_flag) - epoch) >= 0;
-      uint32_t ready = __ballot_sync(kAll, rdy);
-      if (!ready) {
-        if ((++spins & 0x3FFu) == 0) {
-          const uint64_t now = globaltimer_ns();
-          if (t0 == 0) t0 = now;
-          const bool aborted = *reinterpret_cast<const volatile uint32_t*>(p.abort_word) != 0;
-          if (__any_sync(kAll, aborted || now - t0 > p.timeout_ns)) {
-            if (wl == (uint32_t)__ffs(pending) - 1u)
-              *p.status = (aborted ? (uint32_t)kSraAborted : (uint32_t)kSraTimeoutPhase2) |
-                          ((uint32_t)((r + (int)wl) % W) << 8) | ((uint32_t)lane << 16);
-            break;
-          }
-        }
-        continue;
-      }
-      pending &= ~ready;
-      trace_mark(p.trace, lane, 4);
-      while (ready) {
-        const int s = __ffs(ready) - 1;
-        ready &= ready - 1;
-        const int q = (r + s) % W;
-        const uint32_t rot = __shfl_sync(kAll, my_rot, s);
-        const uint32_t end = li.pre[s + 1];
-        const uint8_t* slot = p.recv2[r] + (size_t)q * p.slot_bytes;
-        const SrcSet ss{slot, 0u, 1, -1};
-        // two items per iteration (ILP), and the packed words of the NEXT two are in flight while
-        // these decode
-        auto fetch = [&](uint32_t i, WarpItem& it, SliceWords<GPL>& w) -> bool {
-          if (i >= end) return false;
-          it = lane_item(li, p, i, s);
-          const bool h = item_kind(it) == kItemFull && group_aligned<T>(data + it.elem_off);
-          if (h) slice_fetch<KB, GPL>(slot, it.meta_off, it.pay_off, item_lpb_log2(it), KB ? KB : item_bits(it), w);
-          return h;
-        };
-        auto one = [&](const WarpItem& it, const SliceWords<GPL>& w, bool hot) {
-          const uint32_t kind = item_kind(it);
-          T* blk = data + it.elem_off;
-          if (hot) {
-            full_recv_w<T, KB, GPL, true>(w, it, blk);
-          } else if (kind == kItemFull) {
-            full_recv_unaligned<T, KB, GPL>(ss, it, blk);
-          } else if (kind == kItemRaw && group_aligned<T>(blk)) {
-            float x[2][8];
-            raw_full_x<T, 2, 2>(x, blk, it, 1.0f, ss, none);
-          } else if (kind == kItemBucket) {
-            bucket_recv<T>(ss, it, blk);
-          } else {
-            raw_generic<T>(blk, it, 1.0f, ss, none, 2);
-          }
-        };
-        uint32_t i = li.pre[s] + ((warp - rot) & (kSraWarps - 1));
-        WarpItem ita, itb, na, nb;
-        SliceWords<GPL> wa, wb, wna, wnb;
-        bool hota = fetch(i, ita, wa), hotb = fetch(i + kSraWarps, itb, wb);
-        while (i < end) {
-          const uint32_t in = i + 2 * kSraWarps;
-          const bool hna = fetch(in, na, wna), hnb = fetch(in + kSraWarps, nb, wnb);
-          if (hota && hotb) {
-            full_recv_pair<T, KB, GPL>(wa, wb, ita, itb, data + ita.elem_off, data + itb.elem_off);
-          } else {
-            one(ita, wa, hota);
-            if (i + kSraWarps < end) one(itb, wb, hotb);
-          }
-          ita = na;
-          itb = nb;
-          CGX_COPY_WORDS(wa, wna);
-          CGX_COPY_WORDS(wb, wnb);
-          hota = hna;
-          hotb = hnb;
-          i = in;
-        }
-      }
-    }
-  }
-  trace_mark(p.trace, lane, 5);
-  sync_finish(p.sync, epoch, G);
+  if (!s_abort) sra_phase_c<T, KB, GPL>(p, li, epoch);
+  trace_mark(p, lane, 5);
+  sync_finish(p.sync, epoch, p.lanes);
 }
 
 // ===========================================================================
@@ -401,7 +423,7 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
   rng.stream = (uint32_t)r * 2u;
   if (threadIdx.x == 0) s_abort = 0;
   lane_items_load(li, p, 1);
-  trace_mark(p.trace, lane, 0, true);
+  trace_mark(p, lane, 0, true);
   const uint32_t region = (epoch & 1u) * p.os_parity_stride;
   const uint32_t total = li.pre[1];
   const SrcSet no_src{nullptr, 0u, 0, -1};
@@ -434,7 +456,7 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
     __syncthreads();
     if (warp == 0) signal_peers(p.flags1, W, r, p.flag_stride, lane, epoch);
   }
-  trace_mark(p.trace, lane, 1);
+  trace_mark(p, lane, 1);
 
   // ---- phase 2: all W images (mine was written by this CTA, ordered by the bar.sync above)
   {
@@ -442,7 +464,7 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
       if (!wait_peers(p.flags1[r], p, lane, epoch, kSraTimeoutPhase1)) s_abort = 1;
     }
     __syncthreads();
-    trace_mark(p.trace, lane, 2);
+    trace_mark(p, lane, 2);
     if (!s_abort) {
       const SrcSet ss{p.recv1[r] + region, p.slot_bytes, W, -1};
       const OneDst none{nullptr};
@@ -466,7 +488,7 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
       }
     }
   }
-  trace_mark(p.trace, lane, 5);
+  trace_mark(p, lane, 5);
   sync_finish(p.sync, epoch, p.lanes);
 }
 
