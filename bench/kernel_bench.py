@@ -25,6 +25,7 @@ C = cgx._C
 
 
 def time_op(fn, flush, iters=10, warmup=3):
+    """ONE launch per measurement, L2 flushed before it: includes ~5 us of launch + event overhead."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -39,6 +40,25 @@ def time_op(fn, flush, iters=10, warmup=3):
         ts.append(e0.elapsed_time(e1))
     ts.sort()
     return ts[len(ts) // 2], ts[0]
+
+
+def time_stream(fns, reps=3):
+    """Steady state: the launches of `fns` (each on its OWN buffers, > 2x L2 in total, so nothing is
+    cache resident) back to back between two events; per-launch time, median of `reps`."""
+    for f in fns:
+        f()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for f in fns:
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / len(fns))
+    ts.sort()
+    return ts[len(ts) // 2]
 
 
 def main():
@@ -74,16 +94,30 @@ def main():
                     wb = cgx.ops.wire_bytes(n, bits, bucket, es)
                     tq, tq_min = time_op(lambda: codec.quantize(x, wire), flush)
                     td, td_min = time_op(lambda: codec.dequantize(wire, out), flush)
+                    # steady state over rotating buffer sets (> 2x L2 in total)
+                    nset = max(3, (300 << 20) // (n * es) + 1)
+                    xs = [torch.randn(n, device=dev).to(dtype) for _ in range(nset)]
+                    ws = [torch.zeros(codec.wire_bytes(), dtype=torch.uint8, device=dev) for _ in range(nset)]
+                    os_ = [torch.empty_like(x) for _ in range(nset)]
+                    for a, w in zip(xs, ws):
+                        codec.quantize(a, w)
+                    reps = max(1, 24 // nset)
+                    tqs = time_stream([(lambda a=a, w=w: codec.quantize(a, w)) for a, w in zip(xs, ws)] * reps)
+                    tds = time_stream([(lambda o=o, w=w: codec.dequantize(w, o)) for o, w in zip(os_, ws)] * reps)
+                    del xs, ws, os_
                     g = C.LocalSraGroup(1, args.lanes, max(64 << 20, n * es + (1 << 20)), 5000, 4096)
                     y = x.clone()
                     g.allreduce([y], layers)  # plan + upload outside the timed region
                     tf, tf_min = time_op(lambda: g.allreduce([y], layers), flush)
                     row = {
                         "mb": mb, "dtype": dname, "bits": bits, "bucket": bucket,
-                        "quantize_us": round(tq * 1e3, 1), "quantize_gbs": round((n * es + wb) / tq / 1e6, 1),
-                        "quantize_frac_of_measured_hbm": round((n * es + wb) / tq / 1e6 / hbm, 3),
-                        "dequantize_us": round(td * 1e3, 1), "dequantize_gbs": round((n * es + wb) / td / 1e6, 1),
-                        "dequantize_frac_of_measured_hbm": round((n * es + wb) / td / 1e6 / hbm, 3),
+                        "quantize_stream_us": round(tqs * 1e3, 1),
+                        "quantize_stream_gbs": round((n * es + wb) / tqs / 1e6, 1),
+                        "quantize_stream_frac_of_measured_hbm": round((n * es + wb) / tqs / 1e6 / hbm, 3),
+                        "dequantize_stream_us": round(tds * 1e3, 1),
+                        "dequantize_stream_gbs": round((n * es + wb) / tds / 1e6, 1),
+                        "dequantize_stream_frac_of_measured_hbm": round((n * es + wb) / tds / 1e6 / hbm, 3),
+                        "quantize_single_launch_us": round(tq * 1e3, 1), "dequantize_single_launch_us": round(td * 1e3, 1),
                         "fused_w1_us": round(tf * 1e3, 1), "fused_w1_min_us": round(tf_min * 1e3, 1),
                         "fused_w1_gbs": round((2 * n * es) / tf / 1e6, 1),
                         "fused_w1_frac_of_measured_hbm": round((2 * n * es) / tf / 1e6 / hbm, 3),
@@ -95,7 +129,7 @@ def main():
     Path(args.out).parent.mkdir(parents=True, exist_ok=True)
     Path(args.out).write_text(json.dumps({
         "hbm_gbs_measured": hbm, "clocks": clocks,
-        "timing": "CUDA events around ONE launch, median of 10 after 3 warm-ups, 256 MB L2 flush before every timed launch",
+        "timing": "*_stream_*: CUDA events around back-to-back launches over rotating buffer sets (> 2x L2 in total), per launch; *_single_launch_* and fused_w1: events around ONE launch after a 256 MB L2 flush (includes ~5 us launch + event overhead)",
         "rows": rows}, indent=1))
     print(json.dumps({"clocks": clocks}))
 

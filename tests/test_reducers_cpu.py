@@ -119,7 +119,11 @@ def _hier(rank, world):
         n = 30_000
         ins = _inputs(world, n, torch.float32, seed=7)
         t = ins[rank].clone()
+        be.reset_stats()
         dist.all_reduce(t)
+        if os.environ.get("CGX_INTRA_BROADCAST") == "1" and rank % 2 == 0:
+            # leader: intra SRA + cross ring + COMPRESSED broadcast -- a raw broadcast alone would be n * 4 bytes
+            assert be.stats()[3] < 0.8 * n * 4, be.stats()
         exact = sum(ins)
         span = max(float(x.max() - x.min()) for x in ins) * world
         assert (t - exact).abs().max().item() < span / 255 * 8

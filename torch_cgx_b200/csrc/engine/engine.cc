@@ -186,9 +186,22 @@ void AllreduceEngine::allreduce_cuda(void* data, int dtype, int64_t numel, bool 
 
 void AllreduceEngine::allreduce_cpu(void* data, int dtype, int64_t numel, bool average, int explicit_bucket) {
   if (numel <= 0) return;
+  allreduce_cpu_prepared(data, dtype, prepare_cpu(numel, explicit_bucket), average);
+}
+
+AllreduceEngine::CpuCall AllreduceEngine::prepare_cpu(int64_t numel, int explicit_bucket) const {
+  CpuCall c;
+  c.env = CompressionEnv::read();
+  if (numel > 0) c.layers = resolve_layers(numel, cfg_, c.env, explicit_bucket);
+  return c;
+}
+
+void AllreduceEngine::allreduce_cpu_prepared(void* data, int dtype, const CpuCall& call, bool average) {
+  if (call.layers.empty()) return;
   if (!gen_cpu_.ops) throw std::runtime_error("cgx: CPU reducers are not initialised");
-  CompressionEnv env = CompressionEnv::read();
-  run_layers(false, data, dtype, resolve_layers(numel, cfg_, env, explicit_bucket), average, env, nullptr);
+  // one host reduction at a time: the worker thread and a caller-thread CUDA call share counters
+  std::lock_guard<std::mutex> g(cpu_mu_);
+  run_layers(false, data, dtype, call.layers, average, call.env, nullptr);
 }
 
 void AllreduceEngine::allreduce_cuda_layers(void* data, int dtype, const std::vector<LayerSpec>& layers_in,
@@ -306,14 +319,26 @@ void AllreduceEngine::run_layers(bool cuda, void* data, int dtype, std::vector<L
     const float cross_scale = (local_size_ > 1) ? 1.0f : prescale;
     if (cfg_.intra_broadcast && local_size_ > 1) {
       if (local_rank() == 0) g.cross->allreduce(data, dtype, group, env.skip_incomplete, cross_scale, crng, stream);
-      // leaders hand the result to the rest of their node (raw bytes of the group's span)
-      uint64_t lo = ~0ull, hi = 0;
-      for (const LayerSpec& l : group) {
-        lo = std::min<uint64_t>(lo, l.elem_off);
-        hi = std::max<uint64_t>(hi, l.elem_off + l.numel);
+      // leaders hand the result to the rest of their node: packed when the intra-node stage
+      // compresses (reference: Reducer::Broadcast with do_compression && intra_compress_,
+      // mpi_allreduce_operations.cc:171-176, reducer.cc:96-160), raw bytes of the span otherwise
+      bool any_compressed = false;
+      for (const LayerSpec& l : group) any_compressed = any_compressed || l.bits < kRawBits;
+      if (g.intra && cfg_.intra_compress && any_compressed) {
+        RngParams brng = rng;
+        brng.seq = rng.seq ^ 0x20000000u;
+        const uint64_t before = g.intra->bytes_sent();
+        g.intra->broadcast_compressed(data, dtype, group, env.skip_incomplete, 0, brng, stream);
+        stats_.wire_bytes += g.intra->bytes_sent() - before;
+      } else {
+        uint64_t lo = ~0ull, hi = 0;
+        for (const LayerSpec& l : group) {
+          lo = std::min<uint64_t>(lo, l.elem_off);
+          hi = std::max<uint64_t>(hi, l.elem_off + l.numel);
+        }
+        if (hi > lo && g.intra)
+          g.intra->broadcast(static_cast<uint8_t*>(data) + lo * elsize, (size_t)(hi - lo) * elsize, 0, stream);
       }
-      if (hi > lo && g.intra)
-        g.intra->broadcast(static_cast<uint8_t*>(data) + lo * elsize, (size_t)(hi - lo) * elsize, 0, stream);
     } else {
       g.cross->allreduce(data, dtype, group, env.skip_incomplete, cross_scale, crng, stream);
     }

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "../comm/symmetric_heap.h"
@@ -68,6 +69,15 @@ class AllreduceEngine {
 
   // In-place SUM/AVG allreduce of a host buffer through the generic reducers.
   void allreduce_cpu(void* data, int dtype, int64_t numel, bool average, int explicit_bucket);
+  // The same in two steps, for callers that run the reduction on another thread: the environment
+  // and the layer table are read on the CALLING thread (they may change right after the call
+  // returns, e.g. the `compression()` context manager), the work runs later.
+  struct CpuCall {
+    CompressionEnv env;
+    std::vector<LayerSpec> layers;
+  };
+  CpuCall prepare_cpu(int64_t numel, int explicit_bucket) const;
+  void allreduce_cpu_prepared(void* data, int dtype, const CpuCall& call, bool average);
 
   const EngineConfig& config() const { return cfg_; }
   int rank() const { return rank_; }
@@ -131,6 +141,7 @@ class AllreduceEngine {
   GenericPath gen_cuda_, gen_cpu_;
   std::unique_ptr<SymmetricHeap> heap_;
   std::unique_ptr<FusedSra> fused_;
+  std::mutex cpu_mu_;
   uint32_t call_seq_ = 0;
   int lane_cap_ = 0;  // lane cap of the call being issued (0 = none)
   EngineStats stats_;

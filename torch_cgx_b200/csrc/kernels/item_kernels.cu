@@ -40,6 +40,7 @@ quantize_items_kernel(const TS* __restrict__ src, uint32_t base_elem, const Warp
     const uint32_t kind = item_kind(it);
     const TS* s = src + (it.elem_off - base_elem);
     T* o = out ? out + it.elem_off : nullptr;
+    if (i_ + stride_ < count) slice_prefetch_l2<TS, GPL>(src + (next_.elem_off - base_elem));
     if (kind == kItemFull) {
       const bool al = group_aligned<TS>(s) && (o == nullptr || group_aligned<T>(o));
       if (al) {
@@ -77,6 +78,8 @@ dequantize_items_kernel(const uint8_t* __restrict__ wire, const WarpItem* __rest
   CGX_ITEM_LOOP(it) {
     const uint32_t kind = item_kind(it);
     T* o = dst + it.elem_off;
+    if (i_ + stride_ < count && lane_id() < 4u)  // the next item's packed words (<= 1 KB) and meta
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(wire + (lane_id() == 3u ? next_.meta_off : next_.pay_off + lane_id() * 256u)));
     if (kind == kItemFull) {
       if (group_aligned<T>(o)) {
         SliceWords<GPL> w;

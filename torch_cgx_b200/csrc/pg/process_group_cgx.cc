@@ -1,6 +1,7 @@
 #include "process_group_cgx.h"
 
 #include <c10/cuda/CUDACachingAllocator.h>
+#include <c10/cuda/CUDAGraphsC10Utils.h>
 #include <c10/cuda/CUDAGuard.h>
 
 #include <algorithm>
@@ -362,7 +363,9 @@ c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::engine_allreduce(at::Tensor& t, 
                             comm_stream_->stream(), /*overlapped=*/bucket_idx >= 0);
     work->finish_on_stream();
   }
-  if (engine_->has_p2p()) {
+  // (works created while a CUDA graph is being captured are not watched: their events belong to
+  // the graph and must not be queried)
+  if (engine_->has_p2p() && c10::cuda::currentStreamCaptureStatusMayInitCtx() == c10::cuda::CaptureStatus::None) {
     std::lock_guard<std::mutex> g2(fail_mu_);
     inflight_.emplace_back(work);
     if (inflight_.size() > 4096) inflight_.pop_front();
@@ -382,9 +385,12 @@ c10::intrusive_ptr<c10d::Work> ProcessGroupCGX::engine_allreduce_cpu(at::Tensor&
   auto fut = c10::make_intrusive<c10::ivalue::Future>(c10::ListType::create(c10::TensorType::get()));
   at::Tensor tensor = t;
   const int dtype = to_cgx_dtype(t.scalar_type());
-  worker_->submit([this, fut, tensor, dtype, average, bucket_idx]() mutable {
+  // environment + layer table are captured NOW, on the caller's thread (functional.compression()
+  // restores os.environ as soon as this returns)
+  auto call = std::make_shared<AllreduceEngine::CpuCall>(engine_->prepare_cpu(tensor.numel(), bucket_idx));
+  worker_->submit([this, fut, tensor, dtype, average, call]() mutable {
     try {
-      engine_->allreduce_cpu(tensor.data_ptr(), dtype, tensor.numel(), average, bucket_idx);
+      engine_->allreduce_cpu_prepared(tensor.data_ptr(), dtype, *call, average);
       fut->markCompleted(at::IValue(std::vector<at::Tensor>{tensor}));
     } catch (...) {
       fut->setError(std::current_exception());

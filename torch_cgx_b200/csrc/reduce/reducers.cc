@@ -12,9 +12,9 @@ Reducer::~Reducer() {
     if (b.p) ops_->release(b.p);
 }
 
-const Plan& Reducer::plan_for(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete) {
+const Plan& Reducer::plan_for(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete, int world) {
   PlanOptions opt;
-  opt.world = comm_->size();
+  opt.world = world > 0 ? world : comm_->size();
   opt.lanes = 1;  // rank chunks only: one kernel launch per chunk handles all of its blocks
   opt.dtype = dtype;
   opt.skip_incomplete = skip_incomplete;
@@ -60,6 +60,31 @@ void Reducer::broadcast(void* data, size_t bytes, int root, cudaStream_t stream)
     ops.push_back({false, data, bytes, root});
   }
   comm_->exchange(ops, stream);
+}
+
+void Reducer::broadcast_compressed(void* data, int dtype, const std::vector<LayerSpec>& layers, bool skip_incomplete,
+                                   int root, const RngParams& rng, cudaStream_t stream) {
+  const int W = comm_->size(), r = comm_->rank();
+  if (W == 1) return;
+  const Plan& plan = plan_for(layers, dtype, skip_incomplete, 1);  // the whole buffer is one chunk
+  if (plan.blocks.empty()) return;
+  ops_->bind(plan, stream);
+  const uint32_t nb = (uint32_t)plan.blocks.size();
+  const size_t bytes = plan.chunk_wire_bytes[0];
+  uint8_t* wire = scratch(4, row_bytes(plan));
+  std::vector<P2POp> x;
+  if (r == root) {
+    ops_->quantize(data, 0, nb, wire, 1.0f, make_rng_key(rng, root, 2), stream);
+    ops_->dequantize(wire, 0, nb, data, stream);  // the root keeps what the receivers will decode
+    for (int p = 0; p < W; ++p)
+      if (p != root) x.push_back({true, wire, bytes, p});
+    bytes_sent_ += bytes * (uint64_t)(W - 1);
+    comm_->exchange(x, stream);
+  } else {
+    x.push_back({false, wire, bytes, root});
+    comm_->exchange(x, stream);
+    ops_->dequantize(wire, 0, nb, data, stream);
+  }
 }
 
 // ---------------------------------------------------------------------- SRA --

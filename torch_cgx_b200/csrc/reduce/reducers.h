@@ -33,12 +33,19 @@ class Reducer {
   // in-place allreduce of data[T] restricted to `layers`
   virtual void allreduce(void* data, int dtype, const std::vector<LayerSpec>& layers, bool skip_incomplete,
                          float prescale, const RngParams& rng, cudaStream_t stream) = 0;
-  // raw broadcast of `bytes` from group rank `root` (reference: Reducer::Broadcast, reducer.cc:96-160)
+  // raw broadcast of `bytes` from group rank `root`
   void broadcast(void* data, size_t bytes, int root, cudaStream_t stream);
+  // Compressed broadcast of `layers` (reference: Reducer::Broadcast with do_compression,
+  // /root/reference/src/common/reducer.cc:96-160): the root quantizes, decodes its own bytes back
+  // into `data` (so it holds exactly what every receiver will decode) and sends the SAME packed
+  // bytes to every peer; receivers decode. Raw layers travel as T inside the same record.
+  void broadcast_compressed(void* data, int dtype, const std::vector<LayerSpec>& layers, bool skip_incomplete,
+                            int root, const RngParams& rng, cudaStream_t stream);
   uint64_t bytes_sent() const { return bytes_sent_; }
 
  protected:
-  const Plan& plan_for(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete);
+  // world <= 0: one chunk per rank of the communicator; otherwise that many chunks
+  const Plan& plan_for(const std::vector<LayerSpec>& layers, int dtype, bool skip_incomplete, int world = 0);
   uint8_t* scratch(int slot, size_t bytes);  // grow-only scratch buffers of the backend's memory kind
   static size_t row_bytes(const Plan& p) { return ((size_t)p.max_chunk_wire + 255) / 256 * 256; }
   // [first element, one past last element) spanned by the blocks of a chunk / of the whole plan
