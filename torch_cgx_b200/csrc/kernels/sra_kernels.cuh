@@ -81,8 +81,8 @@ __device__ __forceinline__ bool wait_peers(const uint32_t* my_flags, const SraPa
 }
 
 // ---- per-lane item cache ----------------------------------------------------------------
-// The items of ALL chunks of this lane are copied to shared memory once, in the order
-// s = 0 (my own chunk), 1, .., W-1 (chunk (rank + s) % W): an item descriptor then costs one
+// The items of ALL chunks of this lane are copied to shared memory once (TMA bulk copies), in the
+// order s = 0 (my own chunk), 1, .., W-1 (chunk (rank + s) % W): an item descriptor then costs one
 // LDS instead of a dependent global load in front of every data load. Lists longer than the
 // cache (huge messages on few lanes) read the remainder from global memory.
 constexpr uint32_t kSmemItems = 1024;
@@ -91,8 +91,38 @@ struct LaneItems {
   WarpItem items[kSmemItems];
   uint32_t pre[kMaxPeers + 1];   // pre[s]: flat index of the first item of chunk (rank + s) % W
   uint32_t gfirst[kMaxPeers];    // its index in the global item table
+  unsigned long long mbar;       // completion barrier of the bulk copies below
 };
 
+// ---- TMA bulk copy (cp.async.bulk, 1-D): global -> shared, completion on an mbarrier -----------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t tries = 0; !done; ++tries) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && tries > (1u << 24)) __trap();  // a lost copy must not become a silent hang
+  }
+}
+
+// One elected thread issues ONE bulk copy per chunk (each item list is contiguous in the plan
+// table and 16 B granular -- exactly what cp.async.bulk wants); everybody waits on the mbarrier.
 __device__ __forceinline__ void lane_items_load(LaneItems& li, const SraParams& p, int nchunks) {
   const int lane = blockIdx.x, G = p.lanes;
   if (threadIdx.x < (uint32_t)nchunks) {
@@ -101,19 +131,20 @@ __device__ __forceinline__ void lane_items_load(LaneItems& li, const SraParams& 
     li.gfirst[threadIdx.x] = a;
     li.pre[threadIdx.x + 1] = p.item_first[q * G + lane + 1] - a;  // count, turned into a prefix below
   }
+  if (threadIdx.x == 0) mbar_init(&li.mbar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     li.pre[0] = 0;
     for (int s = 0; s < nchunks; ++s) li.pre[s + 1] += li.pre[s];
+    const uint32_t cached = min(li.pre[nchunks], kSmemItems);
+    mbar_expect_tx(&li.mbar, cached * (uint32_t)sizeof(WarpItem));  // 0 bytes: completes at once
+    for (int s = 0; s < nchunks; ++s) {
+      const uint32_t b = li.pre[s], e = min(li.pre[s + 1], kSmemItems);
+      if (e > b) bulk_g2s(&li.items[b], p.items + li.gfirst[s], (e - b) * (uint32_t)sizeof(WarpItem), &li.mbar);
+    }
   }
-  __syncthreads();
-  const uint32_t total = min(li.pre[nchunks], kSmemItems);
-  for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-    int s = 0;
-    while (i >= li.pre[s + 1]) ++s;
-    li.items[i] = p.items[li.gfirst[s] + (i - li.pre[s])];
-  }
-  __syncthreads();
+  __syncthreads();  // the prefix table is complete
+  mbar_wait(&li.mbar, 0);
 }
 // item with flat index i, known to belong to chunk slot s
 __device__ __forceinline__ WarpItem lane_item(const LaneItems& li, const SraParams& p, uint32_t i, int s) {
