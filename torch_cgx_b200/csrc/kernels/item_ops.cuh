@@ -33,26 +33,32 @@ __device__ __forceinline__ bool slice_single_bucket(uint32_t lg) {
 }
 
 // ---- slice <-> registers -------------------------------------------------------------
-// issue the (vector) loads of a slice: lane l gets groups l, l+32, ...; `src` must be group aligned
+// Lane l owns the GPL adjacent pack groups l*GPL .. l*GPL+GPL-1, i.e. GPL*8 consecutive elements
+// (row k of the register tile = group l*GPL + k). Its packed words are then adjacent too.
+template <int GPL>
+__device__ __forceinline__ uint32_t lane_group(int k) {
+  return lane_id() * GPL + (uint32_t)k;
+}
+// issue the (vector) loads of a slice; `src` must be group aligned
 template <typename TS, int GPL>
 __device__ __forceinline__ void slice_load_vec(const TS* __restrict__ src, float (&x)[GPL][8]) {
-  const TS* p = src + lane_id() * 8u;
+  const TS* p = src + lane_id() * (GPL * 8u);
 #pragma unroll
-  for (int k = 0; k < GPL; ++k) load8_vec<TS>(p + k * 256, x[k]);
+  for (int k = 0; k < GPL; ++k) load8_vec<TS>(p + k * 8, x[k]);
 }
 template <typename TS, int GPL>
 __device__ __forceinline__ void slice_load_scalar(const TS* __restrict__ src, float (&x)[GPL][8]) {
-  const TS* p = src + lane_id() * 8u;
+  const TS* p = src + lane_id() * (GPL * 8u);
 #pragma unroll
-  for (int k = 0; k < GPL; ++k) load8_scalar<TS>(p + k * 256, 8, x[k]);
+  for (int k = 0; k < GPL; ++k) load8_scalar<TS>(p + k * 8, 8, x[k]);
 }
 // pull the slice towards L2 without occupying registers (phase B prefetches its next item this way:
 // its registers are taken by the peers' words)
 template <typename TS, int GPL>
 __device__ __forceinline__ void slice_prefetch_l2(const TS* __restrict__ src) {
-  const TS* p = src + lane_id() * 8u;
+  const TS* p = src + lane_id() * (GPL * 8u);
 #pragma unroll
-  for (int k = 0; k < GPL; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + k * 256));
+  for (int k = 0; k < GPL; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + k * 8));
 }
 template <int GPL>
 __device__ __forceinline__ void slice_scale(float (&x)[GPL][8], float prescale) {
@@ -65,13 +71,13 @@ __device__ __forceinline__ void slice_scale(float (&x)[GPL][8], float prescale) 
 }
 template <typename TO, int GPL, bool VEC>
 __device__ __forceinline__ void slice_store(TO* __restrict__ dst, const float (&x)[GPL][8]) {
-  TO* p = dst + lane_id() * 8u;
+  TO* p = dst + lane_id() * (GPL * 8u);
 #pragma unroll
   for (int k = 0; k < GPL; ++k) {
     if (VEC)
-      store8_vec<TO>(p + k * 256, x[k]);
+      store8_vec<TO>(p + k * 8, x[k]);
     else
-      store8_scalar<TO>(p + k * 256, 8, x[k]);
+      store8_scalar<TO>(p + k * 8, 8, x[k]);
   }
 }
 
@@ -101,15 +107,27 @@ __device__ __forceinline__ void slice_meta(const float (&x)[GPL][8], uint32_t lg
       m[k] = m0;
       inv[k] = i0;
     }
-  } else {
+  } else if (lg == 0) {  // 8-element buckets: every row is its own bucket
 #pragma unroll
     for (int k = 0; k < GPL; ++k) {
-      if (lg >= 5)
-        warp_minmax(mn[k], mx[k]);
-      else
-        subwarp_minmax(mn[k], mx[k], lg);
       m[k] = make_meta(mn[k], mx[k], bits);
       inv[k] = inv_unit(m[k].unit);
+    }
+  } else {
+    // (512-slices only) a bucket of 2^lg groups = all rows of 2^(lg-1) adjacent lanes
+    float a = mn[0], b = mx[0];
+#pragma unroll
+    for (int k = 1; k < GPL; ++k) {
+      a = nan_min(a, mn[k]);
+      b = nan_max(b, mx[k]);
+    }
+    subwarp_minmax(a, b, lg - 1u);
+    const BucketMeta m0 = make_meta(a, b, bits);
+    const float i0 = inv_unit(m0.unit);
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) {
+      m[k] = m0;
+      inv[k] = i0;
     }
   }
 }
@@ -122,7 +140,7 @@ __device__ __forceinline__ void slice_store_meta(const BucketMeta (&m)[GPL], uin
   } else {
 #pragma unroll
     for (int k = 0; k < GPL; ++k) {
-      const uint32_t gi = (uint32_t)k * 32u + lane_id();
+      const uint32_t gi = lane_group<GPL>(k);
       if ((gi & ((1u << lg) - 1u)) == 0)
         dst_st_v2(ds, meta_off + (gi >> lg) * 8u, __float_as_uint(m[k].unit), __float_as_uint(m[k].min));
     }
@@ -138,9 +156,10 @@ __device__ __forceinline__ void slice_encode_mode(const float (&x)[GPL][8], cons
                                                   uint32_t first_elem, const DST& ds, uint32_t pay_off,
                                                   TO* __restrict__ self_out) {
   const float maxlvl = (float)max_level(bits);
+  uint32_t lo[GPL], hi[GPL];
 #pragma unroll
   for (int k = 0; k < GPL; ++k) {
-    const uint32_t gi = (uint32_t)k * 32u + lane_id();
+    const uint32_t gi = lane_group<GPL>(k);
     float u[8];
     if (MODE == 2) {
       float r[8];
@@ -151,9 +170,7 @@ __device__ __forceinline__ void slice_encode_mode(const float (&x)[GPL][8], cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) u[j] = level_magic<MODE == 1>(x[k][j], m[k].min, inv[k], 0.5f, maxlvl);
     }
-    uint32_t lo, hi;
-    pack_magic<KB>(u, bits, lo, hi);
-    store_word<KB>(ds, pay_off, gi, bits, lo, hi);
+    pack_magic<KB>(u, bits, lo[k], hi[k]);
     if (SELF) {
       float dec[8];
 #pragma unroll
@@ -164,6 +181,7 @@ __device__ __forceinline__ void slice_encode_mode(const float (&x)[GPL][8], cons
         store8_scalar<TO>(self_out + gi * 8u, 8, dec);
     }
   }
+  store_words<KB, GPL>(ds, pay_off, bits, lo, hi);
 }
 
 template <typename TO, int KB, int GPL, bool SELF, bool VEC, typename DST>
@@ -196,8 +214,7 @@ struct SliceWords {
 template <int KB, int GPL>
 __device__ __forceinline__ void slice_fetch(const uint8_t* rec, uint32_t meta_off, uint32_t pay_off, uint32_t lg,
                                             int bits, SliceWords<GPL>& w) {
-#pragma unroll
-  for (int k = 0; k < GPL; ++k) load_word<KB>(rec + pay_off, (uint32_t)k * 32u + lane_id(), bits, w.lo[k], w.hi[k]);
+  load_words<KB, GPL>(rec + pay_off, bits, w.lo, w.hi);
   if (slice_single_bucket<GPL>(lg)) {
     const uint2 v = ld_sys_v2(rec + meta_off);
 #pragma unroll
@@ -208,7 +225,7 @@ __device__ __forceinline__ void slice_fetch(const uint8_t* rec, uint32_t meta_of
   } else {
 #pragma unroll
     for (int k = 0; k < GPL; ++k) {
-      const uint2 v = ld_sys_v2(rec + meta_off + ((((uint32_t)k * 32u + lane_id()) >> lg) * 8u));
+      const uint2 v = ld_sys_v2(rec + meta_off + ((lane_group<GPL>(k) >> lg) * 8u));
       w.pm[k].unit = __uint_as_float(v.x);
       w.pm[k].min = __uint_as_float(v.y);
     }
@@ -251,9 +268,7 @@ __device__ __forceinline__ void slice_accumulate(const SrcSet& ss, uint32_t meta
         const int i = min(i0 + u, cnt - 1);
         const int q = (ss.skip >= 0 && i >= ss.skip) ? i + 1 : i;
         const uint8_t* rec = ss.base + (size_t)q * ss.stride;
-#pragma unroll
-        for (int k = 0; k < GPL; ++k)
-          load_word<KB>(rec + pay_off, (uint32_t)k * 32u + lane_id(), bits, lo[u][k], hi[u][k]);
+        load_words<KB, GPL>(rec + pay_off, bits, lo[u], hi[u]);
         const uint2 v = ld_sys_v2(rec + meta_off);
         un[u] = __uint_as_float(v.x);
         mi[u] = __uint_as_float(v.y);
@@ -389,21 +404,20 @@ __device__ __forceinline__ bool full_send_pair(float (&xa)[GPL][8], float (&xb)[
   if (finite) {
     // interleave by rows so that both items' chains are in flight together
     const float maxa = (float)max_level(bits_a), maxb = (float)max_level(bits_b);
+    uint32_t loa[GPL], hia[GPL], lob[GPL], hib[GPL];
 #pragma unroll
     for (int k = 0; k < GPL; ++k) {
-      const uint32_t gi = (uint32_t)k * 32u + lane_id();
       float ua[8], ub[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         ua[j] = level_magic<false>(xa[k][j], ma.min, ia, 0.5f, maxa);
         ub[j] = level_magic<false>(xb[k][j], mb.min, ib, 0.5f, maxb);
       }
-      uint32_t loa, hia, lob, hib;
-      pack_magic<KB>(ua, bits_a, loa, hia);
-      pack_magic<KB>(ub, bits_b, lob, hib);
-      store_word<KB>(dsa, ita.pay_off, gi, bits_a, loa, hia);
-      store_word<KB>(dsb, itb.pay_off, gi, bits_b, lob, hib);
+      pack_magic<KB>(ua, bits_a, loa[k], hia[k]);
+      pack_magic<KB>(ub, bits_b, lob[k], hib[k]);
     }
+    store_words<KB, GPL>(dsa, ita.pay_off, bits_a, loa, hia);
+    store_words<KB, GPL>(dsb, itb.pay_off, bits_b, lob, hib);
   } else {
     slice_encode_mode<float, KB, GPL, false, true, 1>(xa, mav, iav, bits_a, rng, ita.elem_off, dsa, ita.pay_off,
                                                       (float*)nullptr);
@@ -595,7 +609,7 @@ __device__ __forceinline__ void raw_full_x(float (&x)[ROWS][8], T* __restrict__ 
       const uint8_t* rec = ss.base + (size_t)q * ss.stride + it.meta_off;
       float v[2][8];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) raw_wire_load<T>(rec + ((uint32_t)k * 32u + lane_id()) * 8u * sizeof(T), v[k]);
+      for (int k = 0; k < 2; ++k) raw_wire_load<T>(rec + (lane_id() * 2u + (uint32_t)k) * 8u * sizeof(T), v[k]);
 #pragma unroll
       for (int k = 0; k < 2; ++k)
 #pragma unroll
@@ -605,20 +619,20 @@ __device__ __forceinline__ void raw_full_x(float (&x)[ROWS][8], T* __restrict__ 
   if (MODE != 2) {
 #pragma unroll
     for (int k = 0; k < 2; ++k)
-      raw_wire_store<T>(ds, it.meta_off + ((uint32_t)k * 32u + lane_id()) * 8u * (uint32_t)sizeof(T), x[k]);
+      raw_wire_store<T>(ds, it.meta_off + (lane_id() * 2u + (uint32_t)k) * 8u * (uint32_t)sizeof(T), x[k]);
   }
   if (MODE != 0) {
-    T* o = blk + lane_id() * 8u;
+    T* o = blk + lane_id() * 16u;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) store8_vec<T>(o + k * 256, x[k]);
+    for (int k = 0; k < 2; ++k) store8_vec<T>(o + k * 8, x[k]);
   }
 }
 // rows 0..1 of a (possibly larger) register buffer <- the 512 elements of a raw item
 template <typename T, int ROWS>
 __device__ __forceinline__ void raw_load_vec(const T* __restrict__ src, float (&x)[ROWS][8]) {
-  const T* p = src + lane_id() * 8u;
+  const T* p = src + lane_id() * 16u;
 #pragma unroll
-  for (int k = 0; k < 2; ++k) load8_vec<T>(p + k * 256, x[k]);
+  for (int k = 0; k < 2; ++k) load8_vec<T>(p + k * 8, x[k]);
 }
 
 // In-switch reduction of a full raw item (NVLS): every rank staged T(src * prescale) at the same

@@ -368,24 +368,66 @@ __device__ __forceinline__ void load_word(const uint8_t* pay, uint32_t g, int bi
   }
 }
 
-// store the packed word of group g (byte offset `pay_off` of the payload start inside the slot)
-template <int KB, typename DST>
-__device__ __forceinline__ void store_word(const DST& ds, uint32_t pay_off, uint32_t g, int bits, uint32_t lo,
-                                           uint32_t hi) {
-  if constexpr (KB == 8) {
-    dst_st_v2(ds, pay_off + g * 8u, lo, hi);
-  } else if constexpr (KB == 4) {
-    dst_st_u32(ds, pay_off + g * 4u, lo);
-  } else if constexpr (KB == 2) {
-    // two neighbouring groups -> one 32-bit store by the even lane (multimem has no 16-bit form)
-    const uint32_t nb = __shfl_down_sync(kAll, lo, 1);
-    if ((lane_id() & 1u) == 0) dst_st_u32(ds, pay_off + g * 2u, lo | (nb << 16));
+// ---- a lane's words: lane l of the warp owns GPL *adjacent* pack groups (l*GPL .. l*GPL+GPL-1), so
+// its packed words are GPL*KB contiguous bytes: one 4/8/16-byte access per lane, 128-512 contiguous
+// bytes per warp instruction (large NVLink / multimem transactions instead of 4-byte ones).
+template <int KB, int GPL>
+__device__ __forceinline__ void load_words(const uint8_t* pay, int bits, uint32_t (&lo)[GPL], uint32_t (&hi)[GPL]) {
+  const uint32_t g0 = lane_id() * GPL;
+#pragma unroll
+  for (int k = 0; k < GPL; ++k) hi[k] = 0;
+  if constexpr (KB == 4 && GPL == 2) {
+    const uint2 v = ld_sys_v2(pay + (size_t)g0 * 4u);
+    lo[0] = v.x;
+    lo[1] = v.y;
+  } else if constexpr (KB == 8 && GPL == 2) {
+    const uint4 v = ld_sys_v4(pay + (size_t)g0 * 8u);
+    lo[0] = v.x, hi[0] = v.y, lo[1] = v.z, hi[1] = v.w;
+  } else if constexpr (KB == 2 && GPL == 2) {
+    const uint32_t v = ld_sys_u32(pay + (size_t)g0 * 2u);
+    lo[0] = v & 0xFFFFu;
+    lo[1] = v >> 16;
+  } else if constexpr (KB == 4 && GPL == 4) {
+    const uint4 v = ld_sys_v4(pay + (size_t)g0 * 4u);
+    lo[0] = v.x, lo[1] = v.y, lo[2] = v.z, lo[3] = v.w;
+  } else if constexpr (KB == 8 && GPL == 4) {
+    const uint4 a = ld_sys_v4(pay + (size_t)g0 * 8u), b = ld_sys_v4(pay + (size_t)g0 * 8u + 16u);
+    lo[0] = a.x, hi[0] = a.y, lo[1] = a.z, hi[1] = a.w, lo[2] = b.x, hi[2] = b.y, lo[3] = b.z, hi[3] = b.w;
+  } else if constexpr (KB == 2 && GPL == 4) {
+    const uint2 v = ld_sys_v2(pay + (size_t)g0 * 2u);
+    lo[0] = v.x & 0xFFFFu, lo[1] = v.x >> 16, lo[2] = v.y & 0xFFFFu, lo[3] = v.y >> 16;
   } else {
-    // other widths: byte stores through the unicast mappings (the host never hands out a
-    // multicast alias for plans with such widths)
-    const uint64_t w = (uint64_t)lo | ((uint64_t)hi << 32);
-    const uint32_t o = pay_off + g * (uint32_t)bits;
-    for (int t = 0; t < bits; ++t) dst_st_u8(ds, o + t, (uint32_t)(w >> (8 * t)) & 0xFFu);
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) load_word<0>(pay, g0 + (uint32_t)k, bits, lo[k], hi[k]);
+  }
+}
+
+template <int KB, int GPL, typename DST>
+__device__ __forceinline__ void store_words(const DST& ds, uint32_t pay_off, int bits, const uint32_t (&lo)[GPL],
+                                            const uint32_t (&hi)[GPL]) {
+  const uint32_t g0 = lane_id() * GPL;
+  if constexpr (KB == 4 && GPL == 2) {
+    dst_st_v2(ds, pay_off + g0 * 4u, lo[0], lo[1]);
+  } else if constexpr (KB == 8 && GPL == 2) {
+    dst_st_v4(ds, pay_off + g0 * 8u, make_uint4(lo[0], hi[0], lo[1], hi[1]));
+  } else if constexpr (KB == 2 && GPL == 2) {
+    dst_st_u32(ds, pay_off + g0 * 2u, lo[0] | (lo[1] << 16));
+  } else if constexpr (KB == 4 && GPL == 4) {
+    dst_st_v4(ds, pay_off + g0 * 4u, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+  } else if constexpr (KB == 8 && GPL == 4) {
+    dst_st_v4(ds, pay_off + g0 * 8u, make_uint4(lo[0], hi[0], lo[1], hi[1]));
+    dst_st_v4(ds, pay_off + g0 * 8u + 16u, make_uint4(lo[2], hi[2], lo[3], hi[3]));
+  } else if constexpr (KB == 2 && GPL == 4) {
+    dst_st_v2(ds, pay_off + g0 * 2u, lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16));
+  } else {
+    // other widths: byte stores through the unicast mappings (the host never hands out a multicast
+    // alias for plans with such widths)
+#pragma unroll
+    for (int k = 0; k < GPL; ++k) {
+      const uint64_t w = (uint64_t)lo[k] | ((uint64_t)hi[k] << 32);
+      const uint32_t o = pay_off + (g0 + (uint32_t)k) * (uint32_t)bits;
+      for (int t = 0; t < bits; ++t) dst_st_u8(ds, o + t, (uint32_t)(w >> (8 * t)) & 0xFFu);
+    }
   }
 }
 
