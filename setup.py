@@ -57,6 +57,8 @@ for _d in ("/usr/lib/x86_64-linux-gnu", "/lib/x86_64-linux-gnu"):
         LINK_FLAGS = [f"-L{_d}", "-l:libstdc++.so.6"]
         break
 
+LINK_FLAGS.append("-ldl")  # nvtx3 (header-only) resolves the tool's injection library with dlopen
+
 os.environ.setdefault("MAX_JOBS", str(os.cpu_count() or 4))
 
 setup(

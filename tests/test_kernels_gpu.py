@@ -120,6 +120,19 @@ def test_fused_sra_skip_incomplete_and_stochastic():
     _run_local(4, [(0, n, 2, 512)], n, torch.float32, stochastic=True, seed=11, seq=3)
 
 
+@pytest.mark.parametrize("stages", [1, 2, 3, 4])
+def test_fused_sra_pipelined_stages_match_cpu_oracle(stages, monkeypatch):
+    # the pipeline depth (pieces per chunk, one flag value each) must not change a single bit
+    monkeypatch.setenv("CGX_STAGES", str(stages))
+    n = 1_500_000
+    _run_local(8, [(0, n, 4, 512)], n, torch.float32, repeats=2)
+    _run_local(8, [(0, n, 4, 1024)], n, torch.float32, stochastic=True, seed=5, seq=9)
+    layers = [(0, 4099, 4, 512), (4099, 33, 32, 512), (4132, 100_001, 8, 64), (104_133, 7, 32, 512),
+              (104_140, 90_000, 2, 128), (194_140, 300_000, 32, 512)]
+    _run_local(4, layers, 494_140, torch.bfloat16, lanes=6)
+    _run_local(2, [(0, 3000, 4, 512)], 3000, torch.float16)   # fewer items than stages * warps
+
+
 def test_fused_sra_repeated_calls_and_changing_plans():
     # epochs keep increasing across calls; plans (and lane counts) change between calls
     g = C.LocalSraGroup(4, 16, 4 << 20, 5000, 256)

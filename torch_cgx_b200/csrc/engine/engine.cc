@@ -1,5 +1,7 @@
 #include "engine.h"
 
+#include "../common/nvtx.h"
+
 #include <algorithm>
 #include <stdexcept>
 
@@ -126,6 +128,7 @@ void AllreduceEngine::launch_fused(const Launch& l, void* data, float prescale, 
 void AllreduceEngine::allreduce_cuda(void* data, int dtype, int64_t numel, bool average, int explicit_bucket,
                                      cudaStream_t stream, bool overlapped) {
   if (numel <= 0) return;
+  NvtxRange range("cgx:allreduce_cuda", (uint64_t)numel);
   CompressionEnv env = CompressionEnv::read();
   const bool cacheable = explicit_bucket >= 0 && explicit_bucket < 4096 && nodes() == 1 && fused_ &&
                          cfg_.inner_comm == CommType::kP2P && !cfg_.dummy_compression && cfg_.fake_ratio >= 1.0;
@@ -201,6 +204,7 @@ void AllreduceEngine::allreduce_cpu_prepared(void* data, int dtype, const CpuCal
   if (!gen_cpu_.ops) throw std::runtime_error("cgx: CPU reducers are not initialised");
   // one host reduction at a time: the worker thread and a caller-thread CUDA call share counters
   std::lock_guard<std::mutex> g(cpu_mu_);
+  NvtxRange range("cgx:allreduce_cpu", (uint64_t)call.layers.size());
   run_layers(false, data, dtype, call.layers, average, call.env, nullptr);
 }
 
@@ -311,8 +315,12 @@ void AllreduceEngine::run_layers(bool cuda, void* data, int dtype, std::vector<L
     std::vector<LayerSpec> intra_layers = group;
     if (!cfg_.intra_compress && multi_node)
       for (LayerSpec& l : intra_layers) l.bits = kRawBits;
-    if (local_size_ > 1 || !multi_node) intra_stage(cuda, data, dtype, intra_layers, env.skip_incomplete, prescale, rng, stream);
+    if (local_size_ > 1 || !multi_node) {
+      NvtxRange r1("cgx:intra_node", (uint64_t)intra_layers.size());
+      intra_stage(cuda, data, dtype, intra_layers, env.skip_incomplete, prescale, rng, stream);
+    }
     if (!multi_node) continue;
+    NvtxRange r2("cgx:cross_node", (uint64_t)group.size());
     // ---- stage 2: across nodes (reference: mpi_allreduce_operations.cc:161-183)
     RngParams crng = rng;
     crng.seq = rng.seq ^ 0x40000000u;

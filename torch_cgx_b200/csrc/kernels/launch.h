@@ -49,6 +49,7 @@ struct SraParams {
   int uniform_bits;              // common bits of all compressed items (2/4/8 select a specialised kernel), else 0
   int slice_elems;               // 512 or 1024 (plan.slice_elems)
   int oneshot;                   // 0: three-phase SRA, 1: one-shot
+  int stages;                    // SRA: pieces every chunk is pipelined in (1..4, stages * world <= 32)
 };
 
 constexpr int kSraThreads = 256;

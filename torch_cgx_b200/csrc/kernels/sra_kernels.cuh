@@ -33,8 +33,9 @@
 namespace cgx {
 namespace dev {
 
-// Tracing: per-lane phase timestamps (slot 0: kernel start [min], 1: phase A done,
-// 2: phase B inputs arrived, 3: phase B done, 4: last phase-C wait satisfied, 5: end [max]).
+// Tracing: per-lane phase timestamps (slot 0: kernel start [min], 1: phase A stores issued,
+// 2: phase B inputs arrived, 3: phase B stores issued, 4: last phase-C wait satisfied, 5: end [max],
+// 6 / 7: warp 0 after the release (system fence + flag stores) of phase A / B).
 __device__ __forceinline__ void trace_mark(const SraParams& p, int lane, int slot, bool is_min = false) {
   unsigned long long* trace = p.trace;
   if (trace == nullptr || (threadIdx.x & 31u) != 0) return;
@@ -62,7 +63,7 @@ __device__ __forceinline__ void sync_finish(DeviceSync* sync, uint32_t epoch, in
 // warp 0: publish "this lane finished the phase" to every peer. One fence.acq_rel.sys drains the
 // NVLink stores of the whole CTA (made visible to this warp by the preceding bar.sync).
 __device__ __forceinline__ void signal_peers(uint32_t* const* flags, int W, int r, uint32_t flag_stride, int lane,
-                                             uint32_t epoch) {
+                                             uint32_t epoch /* flag_value() */) {
   const uint32_t wl = lane_id();
   if (wl < (uint32_t)W && (int)wl != r) st_release_sys(flags[wl] + (size_t)r * flag_stride + lane, epoch);
 }
@@ -85,14 +86,27 @@ __device__ __forceinline__ bool wait_peers(const uint32_t* my_flags, const SraPa
 // order s = 0 (my own chunk), 1, .., W-1 (chunk (rank + s) % W): an item descriptor then costs one
 // LDS instead of a dependent global load in front of every data load. Lists longer than the
 // cache (huge messages on few lanes) read the remainder from global memory.
+//
+// Stages: the item list of every chunk is cut into S consecutive pieces. Stage t of the allreduce
+// handles piece t of every chunk and has its own flag value, so the NVLink flight time and the
+// release/acquire round trip of stage t are hidden behind the computation of stage t+1 (a lane
+// pipelines with its peer lanes instead of idling between the phases). The cache is laid out
+// stage-major: segment g = t * W + s holds piece t of chunk slot s.
 constexpr uint32_t kSmemItems = 1024;
+constexpr int kMaxStages = 4;
+constexpr int kMaxSegs = 32;  // S * W <= 32: phase C polls one segment per warp lane
 
 struct LaneItems {
   WarpItem items[kSmemItems];
-  uint32_t pre[kMaxPeers + 1];   // pre[s]: flat index of the first item of chunk (rank + s) % W
-  uint32_t gfirst[kMaxPeers];    // its index in the global item table
+  uint32_t pre[kMaxSegs + 1];    // pre[g]: flat index of the first item of segment g
+  uint32_t gfirst[kMaxSegs];     // its index in the global item table
   unsigned long long mbar;       // completion barrier of the bulk copies below
 };
+
+// Flags only ever grow: stage t of call `epoch` publishes epoch * 4 + t + 1.
+__device__ __forceinline__ uint32_t flag_value(uint32_t epoch, int stage) {
+  return epoch * (uint32_t)kMaxStages + (uint32_t)stage + 1u;
+}
 
 // ---- TMA bulk copy (cp.async.bulk, 1-D): global -> shared, completion on an mbarrier -----------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,19 +135,25 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
   }
 }
 
-// One elected thread issues ONE bulk copy per chunk (each item list is contiguous in the plan
-// table and 16 B granular -- exactly what cp.async.bulk wants); everybody waits on the mbarrier.
-__device__ __forceinline__ void lane_items_load(LaneItems& li, const SraParams& p, int nchunks) {
+// One elected thread issues ONE bulk copy per segment (each piece of an item list is contiguous in
+// the plan table and 16 B granular -- exactly what cp.async.bulk wants); everybody waits on the
+// mbarrier.
+__device__ __forceinline__ void lane_items_load(LaneItems& li, const SraParams& p, int nchunks, int stages) {
   const int lane = blockIdx.x, G = p.lanes;
-  if (threadIdx.x < (uint32_t)nchunks) {
-    const int q = nchunks == 1 ? 0 : (p.rank + (int)threadIdx.x) % p.world;
+  const int nsegs = nchunks * stages;
+  if (threadIdx.x < (uint32_t)nsegs) {
+    const int t = (int)threadIdx.x / nchunks, s = (int)threadIdx.x - t * nchunks;
+    const int q = nchunks == 1 ? 0 : (p.rank + s) % p.world;
     const uint32_t a = p.item_first[q * G + lane];
-    li.gfirst[threadIdx.x] = a;
-    li.pre[threadIdx.x + 1] = p.item_first[q * G + lane + 1] - a;  // count, turned into a prefix below
+    const uint32_t n = p.item_first[q * G + lane + 1] - a;
+    const uint32_t lo = n * (uint32_t)t / (uint32_t)stages, hi = n * (uint32_t)(t + 1) / (uint32_t)stages;
+    li.gfirst[threadIdx.x] = a + lo;
+    li.pre[threadIdx.x + 1] = hi - lo;  // count, turned into a prefix below
   }
   if (threadIdx.x == 0) mbar_init(&li.mbar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
+    const int nchunks = nsegs;  // from here on every segment is its own list
     li.pre[0] = 0;
     for (int s = 0; s < nchunks; ++s) li.pre[s + 1] += li.pre[s];
     const uint32_t cached = min(li.pre[nchunks], kSmemItems);
@@ -146,13 +166,13 @@ __device__ __forceinline__ void lane_items_load(LaneItems& li, const SraParams& 
   __syncthreads();  // the prefix table is complete
   mbar_wait(&li.mbar, 0);
 }
-// item with flat index i, known to belong to chunk slot s
+// item with flat index i, known to belong to segment s
 __device__ __forceinline__ WarpItem lane_item(const LaneItems& li, const SraParams& p, uint32_t i, int s) {
   if (i < kSmemItems) return li.items[i];
   return p.items[li.gfirst[s] + (i - li.pre[s])];
 }
 
-// Fetch item `i` of a flat range (cursor `s` = its chunk slot, only ever moves forward) and, if it
+// Fetch item `i` of a flat range (cursor `s` = its segment, only ever moves forward) and, if it
 // is a hot kind with vector-aligned gradients, issue the loads of its values.
 // hot: 0 cold item (loads its own data)  1 full slice  2 full raw item.
 // Plain scalars / arrays on purpose: a struct here ends up in local memory.
@@ -198,16 +218,18 @@ __device__ __forceinline__ RngKey phase_rng(const SraParams& p, uint32_t epoch, 
 // towards L2. With the in-switch reduction the full raw items of ALL chunks (mine included) are
 // staged locally.
 template <typename T, int KB, int GPL>
-__device__ __forceinline__ void sra_phase_a(const SraParams& p, const LaneItems& li, uint32_t epoch) {
+__device__ __forceinline__ void sra_phase_a(const SraParams& p, const LaneItems& li, uint32_t epoch, int stage) {
   const int r = p.rank, W = p.world;
+  const int seg0 = stage * W;
   const uint32_t warp = threadIdx.x >> 5;
   T* data = reinterpret_cast<T*>(p.data);
   const RngKey rng = phase_rng(p, epoch, 0u);
   const SrcSet no_src{nullptr, 0u, 0, -1};
-  const uint32_t own_end = li.pre[1], total = li.pre[W];
-  const uint32_t begin = p.mc_reduce ? 0u : own_end;
-  auto one = [&](const WarpItem& it, int cs, int hot, float (&x)[GPL][8]) {
+  const uint32_t own_end = li.pre[seg0 + 1], total = li.pre[seg0 + W];
+  const uint32_t begin = p.mc_reduce ? li.pre[seg0] : own_end;
+  auto one = [&](const WarpItem& it, int seg, int hot, float (&x)[GPL][8]) {
     const uint32_t kind = item_kind(it);
+    const int cs = seg - seg0;
     const int dstp = (r + cs) % W;
     T* blk = data + it.elem_off;
     if (p.mc_reduce) {
@@ -233,7 +255,7 @@ __device__ __forceinline__ void sra_phase_a(const SraParams& p, const LaneItems&
     else
       raw_generic<T>(blk, it, p.prescale, no_src, push, 0);
   };
-  int sa = p.mc_reduce ? 0 : 1;
+  int sa = seg0 + (p.mc_reduce ? 0 : 1);
   for (uint32_t i = begin + warp; i < total; i += 2 * kSraWarps) {
     WarpItem ita, itb;
     int hota = 0, hotb = 0, sb;
@@ -254,9 +276,9 @@ __device__ __forceinline__ void sra_phase_a(const SraParams& p, const LaneItems&
       }
     }
     bool done = false;
-    if (hota == 1 && hotb == 1 && !(p.mc_reduce && sa == 0)) {
-      const OneDst pa{p.recv1[(r + sa) % W] + (size_t)r * p.slot_bytes};
-      const OneDst pb{p.recv1[(r + sb) % W] + (size_t)r * p.slot_bytes};
+    if (hota == 1 && hotb == 1 && !(p.mc_reduce && sa == seg0)) {
+      const OneDst pa{p.recv1[(r + sa - seg0) % W] + (size_t)r * p.slot_bytes};
+      const OneDst pb{p.recv1[(r + sb - seg0) % W] + (size_t)r * p.slot_bytes};
       done = full_send_pair<KB, GPL>(xa, xb, ita, itb, p.prescale, rng, pa, pb);
     }
     if (!done) {
@@ -270,16 +292,17 @@ __device__ __forceinline__ void sra_phase_a(const SraParams& p, const LaneItems&
 // ---- phase B: reduce my chunk. The registers of this phase belong to the sources' words (four
 // sources in flight); the NEXT item's own values are only pulled towards L2.
 template <typename T, int KB, int GPL>
-__device__ __forceinline__ void sra_phase_b(const SraParams& p, const LaneItems& li, uint32_t epoch) {
+__device__ __forceinline__ void sra_phase_b(const SraParams& p, const LaneItems& li, uint32_t epoch, int stage) {
   const int r = p.rank, W = p.world;
+  const int seg0 = stage * W;
   const uint32_t warp = threadIdx.x >> 5;
   T* data = reinterpret_cast<T*>(p.data);
   const RngKey rng = phase_rng(p, epoch, 1u);
-  const uint32_t own_end = li.pre[1];
+  const uint32_t own_end = li.pre[seg0 + 1];
   const SrcSet ss{p.recv1[r], p.slot_bytes, W, r};
   const MultiDst ds{p.recv2, p.mc_recv2, (uint32_t)r * p.slot_bytes, W, r, nullptr};
-  for (uint32_t i = warp; i < own_end; i += kSraWarps) {
-    const WarpItem it = lane_item(li, p, i, 0);
+  for (uint32_t i = li.pre[seg0] + warp; i < own_end; i += kSraWarps) {
+    const WarpItem it = lane_item(li, p, i, seg0);
     const uint32_t kind = item_kind(it);
     T* blk = data + it.elem_off;
     const bool al = group_aligned<T>(blk);
@@ -287,7 +310,7 @@ __device__ __forceinline__ void sra_phase_b(const SraParams& p, const LaneItems&
     if (al && kind == kItemFull) slice_load_vec<T, GPL>(blk, x);
     if (al && kind == kItemRaw && !p.mc_reduce) raw_load_vec<T, GPL>(blk, x);
     if (i + kSraWarps < own_end) {
-      const WarpItem itn = lane_item(li, p, i + kSraWarps, 0);
+      const WarpItem itn = lane_item(li, p, i + kSraWarps, seg0);
       if (!(p.mc_reduce && item_kind(itn) == kItemRaw)) slice_prefetch_l2<T, GPL>(data + itn.elem_off);
     }
     if (kind == kItemFull) {
@@ -307,26 +330,27 @@ __device__ __forceinline__ void sra_phase_b(const SraParams& p, const LaneItems&
   }
 }
 
-// ---- phase C: decode every peer's reduced chunk, in order of arrival. Lane s of every warp looks
-// after chunk slot s (polls its flag); rot keeps the round-robin over warps continuous across
-// chunks. Two items per iteration (ILP) with the packed words of the NEXT two already in flight.
+// ---- phase C: decode every peer's reduced chunk, piece by piece in order of arrival. Lane g of
+// every warp looks after segment g (polls the flag of its chunk for the value of its stage); the
+// items of a segment are dealt to the warps by flat index. Two items per iteration (ILP) with the
+// packed words of the NEXT two already in flight.
 template <typename T, int KB, int GPL>
-__device__ __forceinline__ void sra_phase_c(const SraParams& p, const LaneItems& li, uint32_t epoch) {
+__device__ __forceinline__ void sra_phase_c(const SraParams& p, const LaneItems& li, uint32_t epoch, int stages) {
   const int lane = blockIdx.x;
   const int r = p.rank, W = p.world;
   const uint32_t warp = threadIdx.x >> 5, wl = threadIdx.x & 31u;
   T* data = reinterpret_cast<T*>(p.data);
-  const uint32_t own_end = li.pre[1];
-  const bool mine = wl >= 1 && wl < (uint32_t)W;
+  const int my_stage = (int)wl / W, my_slot = (int)wl - my_stage * W;
+  const bool mine = my_slot >= 1 && my_stage < stages;
   const uint32_t my_cnt = mine ? li.pre[wl + 1] - li.pre[wl] : 0u;
-  const uint32_t my_rot = mine ? li.pre[wl] - own_end : 0u;
-  const uint32_t* my_flag = p.flags2[r] + (size_t)((r + (int)wl) % W) * p.flag_stride + lane;
+  const uint32_t my_target = flag_value(epoch, my_stage);
+  const uint32_t* my_flag = p.flags2[r] + (size_t)((r + my_slot) % W) * p.flag_stride + lane;
   uint32_t pending = __ballot_sync(kAll, my_cnt > 0);
   uint32_t spins = 0;
   uint64_t t0 = 0;
   const OneDst none{nullptr};
   while (pending) {
-    const bool rdy = ((pending >> wl) & 1u) && (int32_t)(ld_acquire_sys(my_flag) - epoch) >= 0;
+    const bool rdy = ((pending >> wl) & 1u) && (int32_t)(ld_acquire_sys(my_flag) - my_target) >= 0;
     uint32_t ready = __ballot_sync(kAll, rdy);
     if (!ready) {
       if ((++spins & 0x3FFu) == 0) {
@@ -336,7 +360,7 @@ __device__ __forceinline__ void sra_phase_c(const SraParams& p, const LaneItems&
         if (__any_sync(kAll, aborted || now - t0 > p.timeout_ns)) {
           if (wl == (uint32_t)__ffs(pending) - 1u)
             *p.status = (aborted ? (uint32_t)kSraAborted : (uint32_t)kSraTimeoutPhase2) |
-                        ((uint32_t)((r + (int)wl) % W) << 8) | ((uint32_t)lane << 16);
+                        ((uint32_t)((r + my_slot) % W) << 8) | ((uint32_t)lane << 16);
           break;
         }
       }
@@ -345,10 +369,9 @@ __device__ __forceinline__ void sra_phase_c(const SraParams& p, const LaneItems&
     pending &= ~ready;
     trace_mark(p, lane, 4);
     while (ready) {
-      const int s = __ffs(ready) - 1;
+      const int s = __ffs(ready) - 1;  // segment
       ready &= ready - 1;
-      const int q = (r + s) % W;
-      const uint32_t rot = __shfl_sync(kAll, my_rot, s);
+      const int q = (r + __shfl_sync(kAll, my_slot, s)) % W;
       const uint32_t end = li.pre[s + 1];
       const uint8_t* slot = p.recv2[r] + (size_t)q * p.slot_bytes;
       const SrcSet ss{slot, 0u, 1, -1};
@@ -375,7 +398,7 @@ __device__ __forceinline__ void sra_phase_c(const SraParams& p, const LaneItems&
           raw_generic<T>(blk, it, 1.0f, ss, none, 2);
         }
       };
-      uint32_t i = li.pre[s] + ((warp - rot) & (kSraWarps - 1));
+      uint32_t i = li.pre[s] + ((warp - li.pre[s]) & (kSraWarps - 1));
       WarpItem ita, itb, na, nb;
       SliceWords<GPL> wa, wb, wna, wnb;
       bool hota = fetch(i, ita, wa), hotb = fetch(i + kSraWarps, itb, wb);
@@ -406,26 +429,37 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) sra_kernel(const _
   __shared__ int s_abort;
   const int lane = blockIdx.x;
   const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(&p.sync->epoch) + 1u;
+  const int stages = p.stages;
   if (threadIdx.x == 0) s_abort = 0;
-  lane_items_load(li, p, p.world);
+  lane_items_load(li, p, p.world, stages);
   trace_mark(p, lane, 0, true);
 
-  sra_phase_a<T, KB, GPL>(p, li, epoch);
-  __syncthreads();
-  if (threadIdx.x < 32) signal_peers(p.flags1, p.world, p.rank, p.flag_stride, lane, epoch);
-  trace_mark(p, lane, 1);
-
-  if (threadIdx.x < 32 && li.pre[1] > 0) {
-    if (!wait_peers(p.flags1[p.rank], p, lane, epoch, kSraTimeoutPhase1)) s_abort = 1;
+  _Pragma("unroll 1") for (int t = 0; t < stages; ++t) {
+    sra_phase_a<T, KB, GPL>(p, li, epoch, t);
+    __syncthreads();
+    trace_mark(p, lane, 1);
+    if (threadIdx.x < 32) {
+      signal_peers(p.flags1, p.world, p.rank, p.flag_stride, lane, flag_value(epoch, t));
+      trace_mark(p, lane, 6);
+    }
   }
-  __syncthreads();
-  trace_mark(p, lane, 2);
-  if (!s_abort) sra_phase_b<T, KB, GPL>(p, li, epoch);
-  __syncthreads();
-  if (threadIdx.x < 32 && !s_abort) signal_peers(p.flags2, p.world, p.rank, p.flag_stride, lane, epoch);
-  trace_mark(p, lane, 3);
 
-  if (!s_abort) sra_phase_c<T, KB, GPL>(p, li, epoch);
+  _Pragma("unroll 1") for (int t = 0; t < stages; ++t) {
+    if (threadIdx.x < 32 && li.pre[t * p.world + 1] > li.pre[t * p.world]) {
+      if (!wait_peers(p.flags1[p.rank], p, lane, flag_value(epoch, t), kSraTimeoutPhase1)) s_abort = 1;
+    }
+    __syncthreads();
+    trace_mark(p, lane, 2);
+    if (!s_abort) sra_phase_b<T, KB, GPL>(p, li, epoch, t);
+    __syncthreads();
+    trace_mark(p, lane, 3);
+    if (threadIdx.x < 32 && !s_abort) {
+      signal_peers(p.flags2, p.world, p.rank, p.flag_stride, lane, flag_value(epoch, t));
+      trace_mark(p, lane, 7);
+    }
+  }
+
+  if (!s_abort) sra_phase_c<T, KB, GPL>(p, li, epoch, stages);
   trace_mark(p, lane, 5);
   sync_finish(p.sync, epoch, p.lanes);
 }
@@ -453,7 +487,7 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
   rng.seq += epoch - p.epoch_hint;
   rng.stream = (uint32_t)r * 2u;
   if (threadIdx.x == 0) s_abort = 0;
-  lane_items_load(li, p, 1);
+  lane_items_load(li, p, 1, 1);
   trace_mark(p, lane, 0, true);
   const uint32_t region = (epoch & 1u) * p.os_parity_stride;
   const uint32_t total = li.pre[1];
@@ -485,14 +519,14 @@ __global__ void __launch_bounds__(kSraThreads, kSraCtasPerSm) oneshot_kernel(con
         raw_generic<T>(blk, it, p.prescale, no_src, ds, 0);
     }
     __syncthreads();
-    if (warp == 0) signal_peers(p.flags1, W, r, p.flag_stride, lane, epoch);
+    if (warp == 0) signal_peers(p.flags1, W, r, p.flag_stride, lane, flag_value(epoch, 0));
   }
   trace_mark(p, lane, 1);
 
   // ---- phase 2: all W images (mine was written by this CTA, ordered by the bar.sync above)
   {
     if (warp == 0 && total > 0) {
-      if (!wait_peers(p.flags1[r], p, lane, epoch, kSraTimeoutPhase1)) s_abort = 1;
+      if (!wait_peers(p.flags1[r], p, lane, flag_value(epoch, 0), kSraTimeoutPhase1)) s_abort = 1;
     }
     __syncthreads();
     trace_mark(p, lane, 2);

@@ -16,6 +16,7 @@ FusedSra::FusedSra(SymmetricHeap* heap, int max_lanes, int64_t timeout_ms, uint3
   // the heap's multicast mapping altogether; CGX_NVLS_REDUCE=0 keeps the two-shot raw path)
   use_mc_ = heap_->has_multicast() && heap_->world() > 1;
   use_mc_reduce_ = use_mc_ && env_bool("CGX_NVLS_REDUCE", true);
+  stages_ = (int)env_int("CGX_STAGES", 0);  // pipeline depth experiment, see pick_stages()
   if (max_lanes_ < 1) max_lanes_ = 1;
   if ((uint32_t)max_lanes_ > heap_->layout().flag_stride) max_lanes_ = (int)heap_->layout().flag_stride;
 }
@@ -115,6 +116,20 @@ void FusedSra::run_oneshot(const DevicePlan& dp, void* data, float prescale, con
   launch(dp, data, prescale, rng, stream, true);
 }
 
+// Pipeline depth of the fused kernel: every chunk's item list can be cut into S pieces, each with
+// its own flag value, so that the NVLink flight of one piece overlaps the computation of the next.
+// Measured on 2xB200 (profiles/r2/stages_2gpu.md) this LOSES: every extra stage costs one more
+// fence.acq_rel.sys per phase, and a system fence issued while the SM keeps streaming peer stores
+// only completes when that traffic drains (64 MB 4-bit: 64 us at S=1, 77 us at S=2, 123 us at S=4).
+// The default therefore stays 1; CGX_STAGES=2..4 keeps the experiment reproducible.
+int FusedSra::pick_stages(const DevicePlan&) const {
+  const int w = world();
+  const int cap = w > 0 ? (32 / w < 4 ? 32 / w : 4) : 1;
+  int s = stages_ <= 0 ? 1 : stages_;
+  if (s > cap) s = cap;
+  return s < 1 ? 1 : s;
+}
+
 void FusedSra::launch(const DevicePlan& dp, void* data, float prescale, const RngParams& rng, cudaStream_t stream,
                       bool oneshot) {
   if (!heap_->connected()) throw std::runtime_error("cgx: symmetric heap is not connected");
@@ -165,6 +180,7 @@ void FusedSra::launch(const DevicePlan& dp, void* data, float prescale, const Rn
   p.uniform_bits = dp.plan.uniform_bits;
   p.slice_elems = (int)dp.plan.slice_elems;
   p.oneshot = oneshot ? 1 : 0;
+  p.stages = oneshot ? 1 : pick_stages(dp);
   cuda_check(launch_sra_fused(p, stream), "launch_sra_fused");
   ++launches_;
 }

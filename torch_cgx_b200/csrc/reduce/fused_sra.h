@@ -79,6 +79,8 @@ class FusedSra {
   uint32_t epoch_ = 0;  // host mirror of the device-side call counter (DeviceSync)
   uint64_t launches_ = 0;
   bool use_mc_ = false;      // NVLS stores (multimem.st) for phase B / one-shot
+  int stages_ = 0;              // CGX_STAGES override of the pipeline depth (0 = automatic)
+  int pick_stages(const DevicePlan& dp) const;
   bool use_mc_reduce_ = false;  // NVLS in-switch reduction (multimem.ld_reduce) for raw items
   unsigned long long* d_trace_ = nullptr;
   bool trace_on_ = false;
