@@ -73,7 +73,7 @@ def ncu_summary(rep: Path, title: str, note: str):
             lines.append("")
         except ValueError:
             pass
-    (OUT / f"ncu_{rep.stem.replace('a_prof_', '')}.md").write_text("\n".join(lines))
+    (OUT / f"ncu_{rep.stem.replace('a_prof_', '').replace('f_prof_', '')}.md").write_text("\n".join(lines))
 
 
 def sass():
@@ -147,8 +147,11 @@ def ptx():
 
 if __name__ == "__main__":
     g = ROOT / "gpurun_out"
-    if (g / "a_prof_fused_w1.ncu-rep").exists():
-        ncu_summary(g / "a_prof_fused_w1.ncu-rep", "ncu: fused SRA kernel, world = 1, 64 MiB fp32, 4-bit, bucket 512",
+    fused = g / "f_prof_fused_w1.ncu-rep"   # the newest capture wins
+    if not fused.exists():
+        fused = g / "a_prof_fused_w1.ncu-rep"
+    if fused.exists():
+        ncu_summary(fused, "ncu: fused SRA kernel, world = 1, 64 MiB fp32, 4-bit, bucket 512",
                     "World 1 runs only phase B (load -> min/max -> quantize -> pack -> self-decode -> store): 16 Mi elements, "
                     "64 MiB read + 64 MiB written (the writes mostly stay in the 126 MB L2, hence the small DRAM write figure).")
     if (g / "a_prof_quantize.ncu-rep").exists():
