@@ -101,6 +101,8 @@ struct LaneItems {
   uint32_t pre[kMaxSegs + 1];    // pre[g]: flat index of the first item of segment g
   uint32_t gfirst[kMaxSegs];     // its index in the global item table
   unsigned long long mbar;       // completion barrier of the bulk copies below
+  unsigned long long poll_t0[kSraWarps];  // phase C: when a warp's current flag wait started (0 = not waiting);
+                                          // only touched every 1024 polls, so it lives here, not in a register
 };
 
 // Flags only ever grow: stage t of call `epoch` publishes epoch * 4 + t + 1.
@@ -343,21 +345,31 @@ __device__ __forceinline__ void sra_phase_c(const SraParams& p, const LaneItems&
   const int my_stage = (int)wl / W, my_slot = (int)wl - my_stage * W;
   const bool mine = my_slot >= 1 && my_stage < stages;
   const uint32_t my_cnt = mine ? li.pre[wl + 1] - li.pre[wl] : 0u;
-  const uint32_t my_target = flag_value(epoch, my_stage);
   const uint32_t* my_flag = p.flags2[r] + (size_t)((r + my_slot) % W) * p.flag_stride + lane;
   uint32_t pending = __ballot_sync(kAll, my_cnt > 0);
   uint32_t spins = 0;
-  uint64_t t0 = 0;
+  volatile unsigned long long* t0 = &const_cast<LaneItems&>(li).poll_t0[warp];
+  if (wl == 0) *t0 = 0;
+  __syncwarp();
   const OneDst none{nullptr};
   while (pending) {
-    const bool rdy = ((pending >> wl) & 1u) && (int32_t)(ld_acquire_sys(my_flag) - my_target) >= 0;
+    // the flag value this lane waits for is re-derived on every poll (three compares) instead of
+    // occupying a register for the whole phase
+    uint32_t w2 = wl;
+    asm volatile("" : "+r"(w2));
+    const int st = (int)(w2 >= (uint32_t)W) + (int)(w2 >= 2u * (uint32_t)W) + (int)(w2 >= 3u * (uint32_t)W);
+    const bool rdy = ((pending >> wl) & 1u) && (int32_t)(ld_acquire_sys(my_flag) - flag_value(epoch, st)) >= 0;
     uint32_t ready = __ballot_sync(kAll, rdy);
     if (!ready) {
       if ((++spins & 0x3FFu) == 0) {
         const uint64_t now = globaltimer_ns();
-        if (t0 == 0) t0 = now;
+        if (*t0 == 0) {
+          __syncwarp();
+          if (wl == 0) *t0 = now;
+          __syncwarp();
+        }
         const bool aborted = *reinterpret_cast<const volatile uint32_t*>(p.abort_word) != 0;
-        if (__any_sync(kAll, aborted || now - t0 > p.timeout_ns)) {
+        if (__any_sync(kAll, aborted || now - *t0 > p.timeout_ns)) {
           if (wl == (uint32_t)__ffs(pending) - 1u)
             *p.status = (aborted ? (uint32_t)kSraAborted : (uint32_t)kSraTimeoutPhase2) |
                         ((uint32_t)((r + my_slot) % W) << 8) | ((uint32_t)lane << 16);
