@@ -3,13 +3,14 @@
 //
 // One warp owns one *item* (common/wire.h) end to end in registers:
 //   full item    a slice of 512 / 1024 elements made of whole power-of-two buckets.
-//                Lane l holds pack groups {l, l+32, ...} (8 consecutive elements each): one
-//                256-bit load per group for fp32, one 128-bit load for fp16 / bf16; per-bucket
-//                min/max with 3-input FMNMX3 + redux.sync (buckets >= 256) or sub-warp
-//                butterflies (buckets 8..128); quantization without a single F2I / I2F
-//                (levels live in the mantissa of 2^23 + q); Horner packing; the packed words
-//                leave as 128 B coalesced stores to peer memory or ONE multimem.st to the NVLS
-//                multicast mapping.
+//                Lane l holds the adjacent pack groups {l*GPL .. l*GPL+GPL-1} (8 consecutive
+//                elements each, GPL = 2 or 4): one 256-bit load per group for fp32, one 128-bit
+//                load for fp16 / bf16; per-bucket min/max with 3-input FMNMX3 + redux.sync
+//                (whole-slice buckets) or sub-warp butterflies (buckets 8..256); quantization
+//                without a single F2I / I2F (levels live in the mantissa of 2^23 + q); shift-add
+//                tree packing; the packed words of a lane are adjacent, so they leave as ONE
+//                4/8/16-byte store per lane (128-512 contiguous bytes per warp instruction) to
+//                peer memory, or as ONE multimem.st to the NVLS multicast mapping.
 //   bucket item  any single bucket (partial tails, sizes that are not powers of two, > 1024):
 //                generic predicated two-pass code, out of line.
 //   raw items    uncompressed elements: classic two-shot allreduce, or in-switch reduction
