@@ -79,6 +79,53 @@ __global__ void __launch_bounds__(256, 2) tma_kernel(uint8_t* dst, size_t total,
   __threadfence_system();
 }
 
+// st8 plus one 8-byte "meta" store per 256-byte run into a separate region (the traffic shape of
+// phase A: a packed slice + its {unit, min} record)
+__global__ void __launch_bounds__(256, 2) store_meta_kernel(uint8_t* dst, uint8_t* meta, size_t total, uint32_t seed) {
+  const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (size_t)gridDim.x * 8;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t v = seed + threadIdx.x;
+  for (size_t off = warp * 256; off + 256 <= total; off += nwarps * 256) {
+    asm volatile("st.global.v2.b32 [%0], {%1,%2};" ::"l"(dst + off + (size_t)lane * 8), "r"(v), "r"(v + 1) : "memory");
+    if (lane == 0) asm volatile("st.global.v2.b32 [%0], {%1,%2};" ::"l"(meta + (off >> 8) * 8), "r"(v), "r"(v) : "memory");
+  }
+  __threadfence_system();
+}
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// The release at the end of a phase, in isolation: every CTA stores `per_cta` bytes to the peer
+// (8-byte stores), then publishes a flag. MODE 0: bar.sync, warp 0 fences (what the fused kernel
+// does); MODE 1: every warp fences its own stores first, then bar.sync, then warp 0 fences;
+// MODE 2: no fence at all (lower bound, not a valid protocol). times[cta] = {start, stores issued, released}.
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) release_kernel(uint8_t* dst, size_t per_cta, uint32_t* flag, uint32_t seed,
+                                                         unsigned long long* times) {
+  const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  unsigned long long t0 = gtime();
+  uint8_t* base = dst + (size_t)blockIdx.x * per_cta;
+  const uint32_t v = seed + threadIdx.x;
+  for (size_t off = (size_t)w * 256; off + 256 <= per_cta; off += 8 * 256)
+    asm volatile("st.global.v2.b32 [%0], {%1,%2};" ::"l"(base + off + (size_t)lane * 8), "r"(v), "r"(v + 1) : "memory");
+  if (MODE == 1) __threadfence_system();
+  __syncthreads();
+  unsigned long long t1 = gtime();
+  if (w == 0) {
+    if (MODE != 2) __threadfence_system();
+    if (lane == 0) asm volatile("st.relaxed.sys.global.b32 [%0], %1;" ::"l"(flag + blockIdx.x), "r"(seed) : "memory");
+    unsigned long long t2 = gtime();
+    if (lane == 0) {
+      times[blockIdx.x * 3 + 0] = t0;
+      times[blockIdx.x * 3 + 1] = t1;
+      times[blockIdx.x * 3 + 2] = t2;
+    }
+  }
+}
+
 // pull: ld.global.v4 from the peer, sum into a register, write one word locally
 __global__ void __launch_bounds__(256, 2) load_kernel(const uint8_t* src, size_t total, uint32_t* sink) {
   const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (size_t)gridDim.x * 8;
@@ -158,8 +205,46 @@ int main(int argc, char** argv) {
         add("tma256", time_us([&] { tma_kernel<256><<<grid, 256, 8 * 2 * 256>>>(dst, total, 1); }, iters));
         add("tma1k", time_us([&] { tma_kernel<1024><<<grid, 256, 8 * 2 * 1024>>>(dst, total, 1); }, iters));
         add("tma4k", time_us([&] { tma_kernel<4096><<<grid, 256, 8 * 2 * 4096>>>(dst, total, 1); }, iters));
+        add("st8+meta", time_us([&] { store_meta_kernel<<<grid, 256>>>(dst, dst + total, total, 1); }, iters));
         add("ld16", time_us([&] { load_kernel<<<grid, 256>>>(dst, total, sink); }, iters));
         CK(cudaGetLastError());
+      }
+    }
+  }
+  // the release in isolation (phase-A shape: 296 CTAs x 24 KB = 7.1 MB)
+  if (peer) {
+    const int grid = 296;
+    unsigned long long* d_times = nullptr;
+    CK(cudaMalloc(&d_times, grid * 3 * sizeof(unsigned long long)));
+    std::vector<unsigned long long> h(grid * 3);
+    const size_t per_ctas[] = {24u << 10, 96u << 10};
+    for (size_t per_cta : per_ctas) {
+      for (int mode = 0; mode < 3; ++mode) {
+        double s_store = 0, s_rel = 0, s_all = 0;
+        const int reps = 20;
+        for (int it = 0; it < reps + 2; ++it) {
+          uint32_t* flag = reinterpret_cast<uint32_t*>(peer + cap - (1u << 20));
+          if (mode == 0) release_kernel<0><<<grid, 256>>>(peer, per_cta, flag, it, d_times);
+          if (mode == 1) release_kernel<1><<<grid, 256>>>(peer, per_cta, flag, it, d_times);
+          if (mode == 2) release_kernel<2><<<grid, 256>>>(peer, per_cta, flag, it, d_times);
+          CK(cudaMemcpy(h.data(), d_times, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+          if (it < 2) continue;
+          unsigned long long first = ~0ull, last = 0;
+          double a = 0, b = 0;
+          for (int c = 0; c < grid; ++c) {
+            a += (double)(h[c * 3 + 1] - h[c * 3 + 0]);
+            b += (double)(h[c * 3 + 2] - h[c * 3 + 1]);
+            first = h[c * 3] < first ? h[c * 3] : first;
+            last = h[c * 3 + 2] > last ? h[c * 3 + 2] : last;
+          }
+          s_store += a / grid / 1e3;
+          s_rel += b / grid / 1e3;
+          s_all += (double)(last - first) / 1e3;
+        }
+        const char* names[] = {"rel_warp0", "rel_allwarps", "rel_none"};
+        printf("%-12s %3zu KB/CTA: stores issued %.2f us, release %.2f us, first start .. last release %.2f us\n", names[mode],
+               per_cta >> 10, s_store / reps, s_rel / reps, s_all / reps);
+        res.push_back({names[mode], "peer", grid, per_cta * grid / 1048576.0, s_rel / reps, s_all / reps});
       }
     }
   }
