@@ -309,16 +309,24 @@ void ProcessGroupCGX::watchdog_loop() {
   while (!watchdog_stop_) {
     watchdog_cv_.wait_for(lk, std::chrono::milliseconds(50));
     if (watchdog_stop_) break;
-    // forget works whose kernel has finished cleanly
-    while (!inflight_.empty()) {
-      auto sp = inflight_.front().lock();
-      if (sp && !sp->gpu_done()) break;
-      inflight_.pop_front();
+    if (!failure_.empty()) {
+      inflight_.clear();  // late arrivals are failed at enqueue time
+      continue;
     }
-    if (!failure_.empty()) continue;
+    // Works whose kernel has finished may only be forgotten once the status word has been seen
+    // clean AFTER they finished: a kernel that gave up writes the status before it exits, so
+    // "done, then clean" proves a clean run, while "clean, then done" would not.
+    size_t done = 0;
+    for (const auto& w : inflight_) {
+      auto sp = w.lock();
+      if (sp && !sp->gpu_done()) break;
+      ++done;
+    }
     lk.unlock();
-    (void)poll_failure();
+    const std::string msg = poll_failure();  // on failure: marks every in-flight work, finished ones included
     lk.lock();
+    if (msg.empty())
+      for (; done > 0 && !inflight_.empty(); --done) inflight_.pop_front();
   }
 }
 
